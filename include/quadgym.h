@@ -1,0 +1,160 @@
+/*
+ * quadgym.h -- C ABI of libquadgym.so: the B200 (sm_100a) batched replacement for the physics +
+ * epilogue of QuadrupedEnv.step() in antopio26/quadruped-gym.
+ *
+ * The reference has no native FFI of its own: its hot path sits behind five `mujoco` entry points
+ * and the Gymnasium reset/step methods.  Each entry point below names the reference interface it
+ * replaces (paths are /root/reference/...):
+ *
+ *   qg_model_load      <- mujoco.MjModel.from_xml_path            src/envs/quadruped.py:59
+ *   qg_batch_create    <- mujoco.MjData(model)                     src/envs/quadruped.py:60
+ *   qg_reset           <- mujoco.mj_resetData + ctrl default       src/envs/quadruped.py:115-139
+ *                         (+ random yaw, src/envs/walking_quad.py:68-75)
+ *   qg_step            <- clip, frame_skip x mujoco.mj_step,       src/envs/quadruped.py:153-182
+ *                         sensordata copy, reward_fns sum,
+ *                         termination_fns any
+ *   qg_get_state /     <- env.data.{qpos,qvel,act,ctrl,time,       src/envs/quadruped.py:164,
+ *   qg_set_state          qacc_warmstart} attribute access         src/envs/walking_quad.py:74,136
+ *   qg_set_reward_table<- env.reward_fns dict                      src/envs/quadruped.py:97,170-175
+ *   qg_set_options     <- max_time / termination_fns               src/envs/quadruped.py:98-100,149-151
+ *                                                                  src/envs/walking_quad.py:152-162
+ *
+ * Conventions: every function returns 0 on success or a negative QG_E* code and never throws;
+ * qg_last_error() gives a thread-local message.  All *_dev pointers are device memory owned by the
+ * caller (torch tensors); the library owns only its internal state planes.  All work is enqueued
+ * on the caller's stream (`stream` is a cudaStream_t passed as void*; NULL = legacy default
+ * stream) with no hidden synchronisation, except the *_host entry points, which synchronise the
+ * stream before returning.  A batch handle is not thread-safe; use one handle per GPU / process.
+ * There is no CPU fallback: without a CUDA device every batch call fails with QG_ECUDA.
+ */
+#ifndef QUADGYM_H
+#define QUADGYM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QG_OK 0
+#define QG_EINVAL (-1)  /* bad argument */
+#define QG_EBLOB (-2)   /* malformed or truncated model blob */
+#define QG_EMODEL (-3)  /* model outside the supported class (free base + 4 legs x 3 z-hinges ...) */
+#define QG_ECUDA (-4)   /* CUDA runtime error (no device, launch failure, out of memory) */
+#define QG_ENOMEM (-5)
+
+#define QG_NQ 19
+#define QG_NV 18
+#define QG_NU 12
+#define QG_NSENSORDATA 33
+#define QG_MAX_TERMS 16
+
+/* fused reward terms (qg_set_reward_table). "sensor" = value in this step's sensordata (lags the
+ * state by one physics step exactly as in the reference), "state" = mjData after the step. */
+enum {
+    QG_TERM_ALIVE = 0,          /* 1.0                                   walking_quad.py:286-290 */
+    QG_TERM_CTRL_SQ = 1,        /* sum(ctrl^2)                           README.md:68-69 */
+    QG_TERM_QVEL_X = 2,         /* state qvel[0]                         README.md:65-66 */
+    QG_TERM_FORWARD = 3,        /* sensor linvel_x * pos_x               dummy_walking_quad.py:11-13 */
+    QG_TERM_DRIFT = 4,          /* |sensor linvel_y * pos_y|             dummy_walking_quad.py:15-17 */
+    QG_TERM_CONTROL_COST = 5,   /* alpha*first_cost+(1-alpha)*|dctrl|^2  walking_quad.py:255-270 (param = alpha) */
+    QG_TERM_ORIENTATION = 6,    /* sensor zaxis_z                        walking_quad.py:237-241 */
+    QG_TERM_HEIGHT_COST = 7,    /* |sensor pos_z - param|                walking_quad.py:243-247 */
+    QG_TERM_POSTURE_COST = 8,   /* ||(ctrl - centres)/nu||               walking_quad.py:249-253 */
+    QG_TERM_EXP_ORIENTATION = 9,/* exp(zaxis_z) - 1                      walking_quad.py:368, math_utils.py:4-5 */
+    QG_TERM_EXP_HEIGHT = 10,    /* exp(|pos_z - param|) - 1              walking_quad.py:369 */
+    QG_NUM_TERMS = 11
+};
+
+typedef struct qg_model qg_model;
+typedef struct qg_batch qg_batch;
+
+/* Sums over all environments and physics steps since the last qg_get_counters(reset=1). */
+typedef struct qg_counters {
+    unsigned long long physics_steps;   /* env * substeps */
+    unsigned long long contacts;        /* active contacts */
+    unsigned long long efc_rows;        /* constraint rows (limits + 4 per contact) */
+    unsigned long long newton_iters;
+    unsigned long long ls_evals;        /* line-search cost evaluations */
+    unsigned long long verts_tested;    /* hull vertices visited by the support search */
+    unsigned long long diverged;        /* envs reset by the non-finite / >1e10 guard */
+    unsigned long long contact_overflow;/* contacts dropped because a lane's table was full */
+    unsigned long long episodes;        /* terminations seen by qg_step */
+} qg_counters;
+
+const char* qg_last_error(void);
+const char* qg_version(void);
+
+/* --- model ------------------------------------------------------------------------------- */
+int qg_model_load(const void* blob, size_t nbytes, qg_model** out);
+void qg_model_destroy(qg_model* m);
+/* sizes[8] = nq nv nu nbody njnt ngeom nmesh nsensordata */
+int qg_model_info(const qg_model* m, int* sizes, double* timestep);
+
+/* --- batch of environments ---------------------------------------------------------------- */
+int qg_batch_create(const qg_model* m, int n_envs, int device, qg_batch** out);
+void qg_batch_destroy(qg_batch* b);
+int qg_batch_num_envs(const qg_batch* b);
+
+/* max_time: episode limit in seconds (time >= max_time -> terminated, quadruped.py:151);
+ * flip_termination: also terminate when sensordata[29] < 0 (walking_quad.py:152-156);
+ * auto_reset: reset terminated envs inside qg_step (obs_dev then holds the reset observation,
+ *             i.e. zeros, and terminal_obs_dev the last one);
+ * solver_iterations / ls_iterations <= 0 keep the model's values capped at the device defaults. */
+int qg_set_options(qg_batch* b, double max_time, int flip_termination, int auto_reset,
+                   int solver_iterations, int ls_iterations);
+
+/* reward = sum_k weights[k] * term(term_ids[k]; params[k]); terms_dev (if given) receives the
+ * weighted values [N, n_terms].  n_terms = 0 gives the reference's default reward 0.0
+ * (quadruped.py:145-147). */
+int qg_set_reward_table(qg_batch* b, int n_terms, const int* term_ids, const double* weights,
+                        const double* params);
+
+/* mask_dev: [N] uint8 (NULL = all).  random_yaw != 0 draws the base yaw ~ U(0, 2pi) from a
+ * counter-based generator keyed on (seed, global env id = env_offset + i, episode index). */
+int qg_reset(qg_batch* b, const uint8_t* mask_dev, uint64_t seed, int random_yaw,
+             long long env_offset, void* stream);
+
+/* action_dev [N,12] f32; obs_dev [N,33] f32; reward_dev [N] f32; terms_dev [N,n_terms] f32 or
+ * NULL; terminated_dev [N] u8; terminal_obs_dev [N,33] f32 or NULL.  One launch runs the whole
+ * frame_skip loop and the sensor / reward / termination / auto-reset epilogue. */
+int qg_step(qg_batch* b, const float* action_dev, int frame_skip, float* obs_dev, float* reward_dev,
+            float* terms_dev, uint8_t* terminated_dev, float* terminal_obs_dev, void* stream);
+
+/* Same call with HOST buffers: H2D of the actions, qg_step, D2H of obs / reward / terminated
+ * through pinned staging buffers, then a stream synchronise.  This is the end-to-end path. */
+int qg_step_host(qg_batch* b, const float* action_host, int frame_skip, float* obs_host,
+                 float* reward_host, uint8_t* terminated_host, void* stream);
+
+/* state in MuJoCo's conventions: qpos [N,19], qvel [N,18], act [N,12], qacc_warmstart [N,18],
+ * time [N] f64, ctrl [N,12]; any pointer may be NULL to skip that field. */
+int qg_get_state(qg_batch* b, float* qpos_dev, float* qvel_dev, float* act_dev, float* warm_dev,
+                 double* time_dev, float* ctrl_dev, void* stream);
+int qg_set_state(qg_batch* b, const float* qpos_dev, const float* qvel_dev, const float* act_dev,
+                 const float* warm_dev, const double* time_dev, const float* ctrl_dev, void* stream);
+
+/* One physics step with stage outputs for parity tests (any output pointer may be NULL):
+ * qacc [N,18] and qacc_smooth [N,18] in MuJoCo's convention (base linear part in the world
+ * frame); qfrc_bias [N,18] and M [N,18,18] in the kernel's "B form" (the three base-linear
+ * dofs expressed in the base body frame: M_B = T^T M T, T = diag(R_base, I_15));
+ * counts [N,4] = ncon, nefc, newton iterations, line-search evaluations; sensordata [N,33].
+ * The state advances exactly as in qg_step with frame_skip = 1 and ctrl_dev [N,12] written to
+ * data.ctrl unclipped (mj_step semantics, not env.step).  Synchronises the stream. */
+int qg_debug_step(qg_batch* b, const float* ctrl_dev, float* qacc_dev, float* qacc_smooth_dev,
+                  float* qfrc_bias_dev, float* M_dev, int* counts_dev, float* sensordata_dev,
+                  void* stream);
+
+int qg_get_counters(qg_batch* b, qg_counters* out_host, int reset, void* stream);
+
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+unsigned long long qg_launch_count(void);
+
+/* FP32 FFMA peak microbenchmark (roofline denominator): runs `iters` dependent-chain
+ * FFMA rounds on every SM and returns the achieved TFLOP/s. */
+int qg_fp32_peak(int device, int iters, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,622 @@
+// qg_api.cu -- C ABI of libquadgym.so (declared in include/quadgym.h): model blob -> device tables,
+// batch state planes in HBM, launches on the caller's stream.  No torch types, no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/quadgym.h"
+#include "qg_kernels.cuh"
+
+static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_OK(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) return fail(QG_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_));     \
+    } while (0)
+
+struct qg_model {
+    QgModelC c;
+    std::vector<float> verts;     // xyz_ per hull vertex
+    std::vector<int> vert_edge;   // per vertex: start of neighbour list relative to the mesh' edge0
+    std::vector<int> mesh_edge;
+    int sizes[8];
+    double timestep;
+};
+
+struct qg_batch {
+    int n, device;
+    QgModelC* d_model;
+    float4* d_verts;
+    int *d_vert_edge, *d_mesh_edge;
+    float4* d_state;
+    QgCounters* d_ctr;
+    QgStepOpts opts;
+    size_t smem;
+    // pinned + device staging for the host-buffer path
+    float *h_act, *h_obs, *h_rew, *d_act, *d_obs, *d_rew;
+    unsigned char *h_term, *d_term;
+};
+
+extern "C" const char* qg_last_error(void) { return g_err; }
+extern "C" const char* qg_version(void) { return "quadgym-b200 0.1 (sm_100a)"; }
+extern "C" unsigned long long qg_launch_count(void) { return g_launches; }
+
+// ------------------------------------------------------------------------------------------ blob
+struct Blob {
+    std::map<std::string, std::vector<double>> f;
+    std::map<std::string, std::vector<int>> i;
+};
+
+static int parse_blob(const void* blob, size_t n, Blob& out) {
+    const unsigned char* b = (const unsigned char*)blob;
+    if (!blob || n < 16 || memcmp(b, "QGBLOB01", 8) != 0) return fail(QG_EBLOB, "bad blob magic");
+    uint32_t nsec;
+    memcpy(&nsec, b + 8, 4);
+    size_t off = 16;
+    for (uint32_t s = 0; s < nsec; ++s) {
+        if (off + 24 > n) return fail(QG_EBLOB, "truncated blob (section header %u)", s);
+        char name[17];
+        memcpy(name, b + off, 16);
+        name[16] = 0;
+        uint32_t code, cnt;
+        memcpy(&code, b + off + 16, 4);
+        memcpy(&cnt, b + off + 20, 4);
+        off += 24;
+        size_t nbytes = (size_t)cnt * (code == 1 ? 8 : 4);
+        if (code != 1 && code != 2) return fail(QG_EBLOB, "section %s: bad dtype %u", name, code);
+        if (off + nbytes > n) return fail(QG_EBLOB, "truncated blob (section %s)", name);
+        if (code == 1) {
+            std::vector<double> v(cnt);
+            memcpy(v.data(), b + off, nbytes);
+            out.f[name] = std::move(v);
+        } else {
+            std::vector<int> v(cnt);
+            memcpy(v.data(), b + off, nbytes);
+            out.i[name] = std::move(v);
+        }
+        off += nbytes + ((8 - nbytes % 8) % 8);
+    }
+    return QG_OK;
+}
+
+static void quat2mat(const double* q, float* R) {
+    double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    double w = q[0] / n, x = q[1] / n, y = q[2] / n, z = q[3] / n;
+    R[0] = (float)(1 - 2 * (y * y + z * z)); R[1] = (float)(2 * (x * y - w * z)); R[2] = (float)(2 * (x * z + w * y));
+    R[3] = (float)(2 * (x * y + w * z)); R[4] = (float)(1 - 2 * (x * x + z * z)); R[5] = (float)(2 * (y * z - w * x));
+    R[6] = (float)(2 * (x * z - w * y)); R[7] = (float)(2 * (y * z + w * x)); R[8] = (float)(1 - 2 * (x * x + y * y));
+}
+
+extern "C" int qg_model_load(const void* blob, size_t nbytes, qg_model** out) {
+    if (!out) return fail(QG_EINVAL, "out is NULL");
+    Blob B;
+    int rc = parse_blob(blob, nbytes, B);
+    if (rc) return rc;
+    static const char* need_f[] = {"opt_f", "body_pos", "body_quat", "body_mass", "body_ipos", "body_inertia",
+                                   "body_invweight0", "jnt_axis", "jnt_pos", "jnt_range", "jnt_solref", "jnt_solimp",
+                                   "qpos0", "dof_damping", "dof_armature", "dof_invweight0", "act_gear", "act_gain",
+                                   "act_bias", "act_tau", "act_ctrlrange", "act_frcrange", "geom_pos", "geom_quat",
+                                   "geom_rbound", "geom_margin", "geom_mu", "geom_solref", "geom_solimp", "mesh_vert"};
+    static const char* need_i[] = {"sizes", "opt_i", "body_parent", "jnt_type", "jnt_body", "jnt_qposadr", "jnt_dofadr",
+                                   "jnt_limited", "dof_body", "act_dof", "act_ctrllimited", "act_frclimited",
+                                   "geom_body", "geom_mesh", "mesh_vertadr", "mesh_vertnum", "mesh_edgeadr",
+                                   "mesh_vert_edge", "mesh_edge"};
+    for (const char* k : need_f)
+        if (!B.f.count(k)) return fail(QG_EBLOB, "missing section %s", k);
+    for (const char* k : need_i)
+        if (!B.i.count(k)) return fail(QG_EBLOB, "missing section %s", k);
+    const std::vector<int>& sz = B.i["sizes"];
+    if (sz.size() != 8) return fail(QG_EBLOB, "bad sizes section");
+    const int nq = sz[0], nv = sz[1], nu = sz[2], nbody = sz[3], njnt = sz[4], ngeom = sz[5], nmesh = sz[6];
+    if (nq != QG_NQ || nv != QG_NV || nbody != 2 + QG_NLEG * QG_NLINK || njnt != 1 + QG_NLEG * QG_NLINK || sz[7] != QG_NSENSORDATA)
+        return fail(QG_EMODEL, "unsupported sizes nq=%d nv=%d nbody=%d njnt=%d (need free base + 4 legs x 3 hinges)", nq, nv, nbody, njnt);
+    auto F = [&](const char* k) -> const std::vector<double>& { return B.f[k]; };
+    auto I = [&](const char* k) -> const std::vector<int>& { return B.i[k]; };
+#define CHECK_LEN(vec, len, name) \
+    if ((int)(vec).size() != (int)(len)) return fail(QG_EBLOB, "section %s: expected %d values, got %d", name, (int)(len), (int)(vec).size());
+    CHECK_LEN(F("opt_f"), 9, "opt_f");
+    CHECK_LEN(I("opt_i"), 5, "opt_i");
+    CHECK_LEN(I("body_parent"), nbody, "body_parent");
+    CHECK_LEN(F("body_pos"), 3 * nbody, "body_pos");
+    CHECK_LEN(F("body_quat"), 4 * nbody, "body_quat");
+    CHECK_LEN(F("body_mass"), nbody, "body_mass");
+    CHECK_LEN(F("body_ipos"), 3 * nbody, "body_ipos");
+    CHECK_LEN(F("body_inertia"), 6 * nbody, "body_inertia");
+    CHECK_LEN(F("body_invweight0"), 2 * nbody, "body_invweight0");
+    CHECK_LEN(I("jnt_type"), njnt, "jnt_type");
+    CHECK_LEN(I("jnt_body"), njnt, "jnt_body");
+    CHECK_LEN(I("jnt_dofadr"), njnt, "jnt_dofadr");
+    CHECK_LEN(I("jnt_qposadr"), njnt, "jnt_qposadr");
+    CHECK_LEN(F("jnt_axis"), 3 * njnt, "jnt_axis");
+    CHECK_LEN(F("jnt_pos"), 3 * njnt, "jnt_pos");
+    CHECK_LEN(F("jnt_range"), 2 * njnt, "jnt_range");
+    CHECK_LEN(I("jnt_limited"), njnt, "jnt_limited");
+    CHECK_LEN(F("qpos0"), nq, "qpos0");
+    CHECK_LEN(F("dof_damping"), nv, "dof_damping");
+    CHECK_LEN(F("dof_armature"), nv, "dof_armature");
+    CHECK_LEN(F("dof_invweight0"), nv, "dof_invweight0");
+    CHECK_LEN(I("act_dof"), nu, "act_dof");
+    CHECK_LEN(F("act_gear"), nu, "act_gear");
+    CHECK_LEN(F("act_gain"), nu, "act_gain");
+    CHECK_LEN(F("act_bias"), 3 * nu, "act_bias");
+    CHECK_LEN(F("act_tau"), nu, "act_tau");
+    CHECK_LEN(F("act_ctrlrange"), 2 * nu, "act_ctrlrange");
+    CHECK_LEN(F("act_frcrange"), 2 * nu, "act_frcrange");
+    CHECK_LEN(I("act_ctrllimited"), nu, "act_ctrllimited");
+    CHECK_LEN(I("act_frclimited"), nu, "act_frclimited");
+    CHECK_LEN(I("geom_body"), ngeom, "geom_body");
+    CHECK_LEN(F("geom_pos"), 3 * ngeom, "geom_pos");
+    CHECK_LEN(F("geom_quat"), 4 * ngeom, "geom_quat");
+    CHECK_LEN(I("geom_mesh"), ngeom, "geom_mesh");
+    CHECK_LEN(F("geom_rbound"), ngeom, "geom_rbound");
+    CHECK_LEN(F("geom_margin"), ngeom, "geom_margin");
+    CHECK_LEN(F("geom_mu"), ngeom, "geom_mu");
+    CHECK_LEN(F("geom_solref"), 2 * ngeom, "geom_solref");
+    CHECK_LEN(F("geom_solimp"), 5 * ngeom, "geom_solimp");
+    CHECK_LEN(I("mesh_vertadr"), nmesh, "mesh_vertadr");
+    CHECK_LEN(I("mesh_vertnum"), nmesh, "mesh_vertnum");
+    CHECK_LEN(I("mesh_edgeadr"), nmesh, "mesh_edgeadr");
+    if (nu > QG_NU) return fail(QG_EMODEL, "too many actuators (%d)", nu);
+
+    qg_model* m = new qg_model();
+    QgModelC& c = m->c;
+    memset(&c, 0, sizeof c);
+    memcpy(m->sizes, sz.data(), sizeof m->sizes);
+    const std::vector<double>& of = F("opt_f");
+    const std::vector<int>& oi = I("opt_i");
+    m->timestep = of[0];
+    c.timestep = (float)of[0];
+    c.timestep_d = of[0];
+    c.grav[0] = (float)of[1]; c.grav[1] = (float)of[2]; c.grav[2] = (float)of[3];
+    c.plane_z = (float)of[7];
+    c.tol = (float)std::fmax(of[4], 1e-6);  // fp32 floor on the solver tolerance ("precision")
+    c.scale = (float)(1.0 / (of[8] * (nv > 1 ? nv : 1)));
+    c.integrator = oi[0];
+    if (oi[1] != 0) { delete m; return fail(QG_EMODEL, "elliptic friction cones are not implemented yet (cone=pyramidal only)"); }
+    if (of[6] != 1.0) { delete m; return fail(QG_EMODEL, "impratio != 1 is not supported"); }
+    c.max_iter = oi[2] < 20 ? oi[2] : 20;
+    c.ls_iter = oi[3] < 12 ? oi[3] : 12;
+    c.rule_first = oi[4];
+
+    // ---- topology: body 1 = free base, then 4 chains of 3 single-hinge bodies
+    const std::vector<int>& bp = I("body_parent");
+    const std::vector<int>& jt = I("jnt_type");
+    const std::vector<int>& jb = I("jnt_body");
+    const std::vector<int>& jd = I("jnt_dofadr");
+    const std::vector<int>& jq = I("jnt_qposadr");
+#define BADMODEL(...) { delete m; return fail(QG_EMODEL, __VA_ARGS__); }
+    if (bp[1] != 0 || jb[0] != 1 || jt[0] != 0 || jd[0] != 0 || jq[0] != 0) BADMODEL("body 1 must be the free-floating base");
+    int body_leg[64], body_level[64];
+    for (int b = 0; b < nbody; ++b) body_leg[b] = -1, body_level[b] = (b == 1 ? 0 : -1);
+    int nleg = 0;
+    std::vector<int> body_joint(nbody, -1);
+    for (int j = 0; j < njnt; ++j) {
+        if (body_joint[jb[j]] >= 0) BADMODEL("body %d has more than one joint", jb[j]);
+        body_joint[jb[j]] = j;
+    }
+    for (int b = 2; b < nbody; ++b) {
+        int p = bp[b];
+        if (p == 1) {
+            if (nleg >= QG_NLEG) BADMODEL("more than %d legs", QG_NLEG);
+            body_leg[b] = nleg++;
+            body_level[b] = 1;
+        } else {
+            if (p < 2 || body_leg[p] < 0 || body_level[p] >= QG_NLINK) BADMODEL("body %d is not part of a 3-link leg chain", b);
+            body_leg[b] = body_leg[p];
+            body_level[b] = body_level[p] + 1;
+            for (int b2 = 2; b2 < b; ++b2)
+                if (b2 != b && bp[b2] == p) BADMODEL("leg links must form a chain (body %d has two children)", p);
+        }
+        int j = body_joint[b];
+        if (j < 0 || jt[j] != 3) BADMODEL("body %d needs exactly one hinge joint", b);
+        int l = body_leg[b], k = body_level[b] - 1;
+        if (jd[j] != 6 + 3 * l + k || jq[j] != 7 + 3 * l + k) BADMODEL("joint %d: dof order must be base, then legs in order", j);
+        const double* ax = &F("jnt_axis")[3 * j];
+        const double* jp = &F("jnt_pos")[3 * j];
+        if (std::fabs(ax[0]) > 1e-9 || std::fabs(ax[1]) > 1e-9 || std::fabs(ax[2] - 1) > 1e-9) BADMODEL("joint %d: hinge axis must be the local z axis", j);
+        if (std::fabs(jp[0]) + std::fabs(jp[1]) + std::fabs(jp[2]) > 1e-12) BADMODEL("joint %d: hinge must pass through the body origin", j);
+        QgJointC& J = c.joint[l][k];
+        for (int i = 0; i < 3; ++i) J.pos[i] = (float)F("body_pos")[3 * b + i];
+        quat2mat(&F("body_quat")[4 * b], J.Roff);
+        for (int i = 0; i < 3; ++i) J.com[i] = (float)F("body_ipos")[3 * b + i];
+        J.mass = (float)F("body_mass")[b];
+        for (int i = 0; i < 6; ++i) J.I[i] = (float)F("body_inertia")[6 * b + i];
+        J.q0 = (float)F("qpos0")[jq[j]];
+        J.lo = (float)F("jnt_range")[2 * j];
+        J.hi = (float)F("jnt_range")[2 * j + 1];
+        J.limited = I("jnt_limited")[j];
+        J.damping = (float)F("dof_damping")[jd[j]];
+        J.armature = (float)F("dof_armature")[jd[j]];
+        J.invw_dof = (float)F("dof_invweight0")[jd[j]];
+    }
+    if (nleg != QG_NLEG) BADMODEL("expected %d legs, found %d", QG_NLEG, nleg);
+    for (int l = 0; l < QG_NLEG; ++l)
+        for (int k = 0; k < QG_NLINK; ++k)
+            if (c.joint[l][k].mass <= 0.f) BADMODEL("leg %d link %d has no mass", l, k);
+    // base
+    c.base_mass = (float)F("body_mass")[1];
+    for (int i = 0; i < 3; ++i) c.base_com[i] = (float)F("body_ipos")[3 + i];
+    for (int i = 0; i < 6; ++i) c.base_I[i] = (float)F("body_inertia")[6 + i];
+    for (int i = 0; i < 6; ++i) { c.base_damp[i] = (float)F("dof_damping")[i]; c.base_arm[i] = (float)F("dof_armature")[i]; }
+    if (c.base_damp[0] != c.base_damp[1] || c.base_damp[0] != c.base_damp[2] || c.base_arm[0] != c.base_arm[1] || c.base_arm[0] != c.base_arm[2])
+        BADMODEL("damping/armature of the base translation must be isotropic");
+    for (int i = 0; i < 19; ++i) c.qpos0[i] = (float)F("qpos0")[i];
+    const double h = of[0];
+    // joint-limit solver parameters
+    {
+        const std::vector<double>& sr = F("jnt_solref");
+        const std::vector<double>& si = F("jnt_solimp");
+        double tc = std::fmax(sr[0], 2 * h), dr = sr[1], dmax = si[1];
+        c.lim_K = (float)(1.0 / std::fmax(1e-15, dmax * dmax * tc * tc * dr * dr));
+        c.lim_B = (float)(2.0 / std::fmax(1e-15, dmax * tc));
+        c.lim_d0 = (float)si[0]; c.lim_dmax = (float)si[1]; c.lim_width = (float)si[2]; c.lim_mid = (float)si[3]; c.lim_power = (float)si[4];
+    }
+    // actuators
+    for (int a = 0; a < nu; ++a) {
+        int dof = I("act_dof")[a];
+        if (dof < 6 || dof >= 18) BADMODEL("actuator %d must act on a leg hinge", a);
+        QgJointC& J = c.joint[(dof - 6) / 3][(dof - 6) % 3];
+        if (J.has_act) BADMODEL("more than one actuator on dof %d", dof);
+        J.has_act = 1;
+        J.gear = (float)F("act_gear")[a];
+        J.kp = (float)F("act_gain")[a];
+        J.b0 = (float)F("act_bias")[3 * a]; J.b1 = (float)F("act_bias")[3 * a + 1]; J.b2 = (float)F("act_bias")[3 * a + 2];
+        double tau = F("act_tau")[a];
+        J.has_dyn = tau > 0;
+        J.inv_tau = tau > 0 ? (float)(1.0 / tau) : 0.f;
+        J.act_fac = tau > 0 ? (float)(tau * (1.0 - std::exp(-h / tau))) : 0.f;
+        J.ctrl_limited = I("act_ctrllimited")[a];
+        J.frc_limited = I("act_frclimited")[a];
+        J.ctrl_lo = (float)F("act_ctrlrange")[2 * a]; J.ctrl_hi = (float)F("act_ctrlrange")[2 * a + 1];
+        J.frc_lo = (float)F("act_frcrange")[2 * a]; J.frc_hi = (float)F("act_frcrange")[2 * a + 1];
+    }
+    // vertex tables
+    const std::vector<double>& mv = F("mesh_vert");
+    int nvert = (int)mv.size() / 3;
+    if (nvert > QG_MAXVERT) BADMODEL("too many hull vertices (%d > %d)", nvert, QG_MAXVERT);
+    CHECK_LEN(I("mesh_vert_edge"), nvert, "mesh_vert_edge");
+    m->verts.resize(4 * (size_t)nvert);
+    for (int i = 0; i < nvert; ++i) {
+        m->verts[4 * i] = (float)mv[3 * i]; m->verts[4 * i + 1] = (float)mv[3 * i + 1]; m->verts[4 * i + 2] = (float)mv[3 * i + 2];
+        m->verts[4 * i + 3] = 0.f;
+    }
+    m->vert_edge = I("mesh_vert_edge");
+    m->mesh_edge = I("mesh_edge");
+    c.nvert = nvert;
+    // geoms: leg geoms to their lane, base geoms to the lane with the fewest geoms so far
+    std::vector<int> lane_of(ngeom), level_of(ngeom);
+    int count[QG_NLEG] = {0, 0, 0, 0};
+    for (int g = 0; g < ngeom; ++g) {
+        int b = I("geom_body")[g];
+        if (b < 1 || b >= nbody) BADMODEL("geom %d: bad body", g);
+        level_of[g] = body_level[b];
+        lane_of[g] = body_leg[b];
+        if (b != 1) count[lane_of[g]]++;
+    }
+    for (int g = 0; g < ngeom; ++g)
+        if (I("geom_body")[g] == 1) {
+            int best = 0;
+            for (int l = 1; l < QG_NLEG; ++l)
+                if (count[l] < count[best]) best = l;
+            lane_of[g] = best;
+            count[best]++;
+        }
+    for (int l = 0; l < QG_NLEG; ++l) {
+        if (count[l] > QG_MAXGEOM_LANE) BADMODEL("too many geoms on lane %d", l);
+        int n = 0;
+        for (int lev = 0; lev <= QG_NLINK; ++lev) {
+            c.glev[l][lev] = n;
+            for (int g = 0; g < ngeom; ++g) {
+                if (lane_of[g] != l || level_of[g] != lev) continue;
+                QgGeomC& G = c.geom[l][n++];
+                int b = I("geom_body")[g], me = I("geom_mesh")[g];
+                for (int i = 0; i < 3; ++i) G.pos[i] = (float)F("geom_pos")[3 * g + i];
+                quat2mat(&F("geom_quat")[4 * g], G.R);
+                int v0 = I("mesh_vertadr")[me], vn = I("mesh_vertnum")[me];
+                double hx = 0, hy = 0, hz = 0;
+                for (int i = v0; i < v0 + vn; ++i) {
+                    hx = std::fmax(hx, std::fabs(mv[3 * i])); hy = std::fmax(hy, std::fabs(mv[3 * i + 1])); hz = std::fmax(hz, std::fabs(mv[3 * i + 2]));
+                }
+                G.half[0] = (float)(hx * 1.0001 + 1e-7); G.half[1] = (float)(hy * 1.0001 + 1e-7); G.half[2] = (float)(hz * 1.0001 + 1e-7);
+                G.margin = (float)F("geom_margin")[g];
+                double mu = F("geom_mu")[g];
+                G.mu = (float)mu;
+                const double* sr = &F("geom_solref")[2 * g];
+                const double* si = &F("geom_solimp")[5 * g];
+                double tc = std::fmax(sr[0], 2 * h), dr = sr[1], dmax = si[1];
+                G.K = (float)(1.0 / std::fmax(1e-15, dmax * dmax * tc * tc * dr * dr));
+                G.B = (float)(2.0 / std::fmax(1e-15, dmax * tc));
+                G.d0 = (float)si[0]; G.dmax = (float)si[1]; G.width = (float)si[2]; G.mid = (float)si[3]; G.power = (float)si[4];
+                double tran = F("body_invweight0")[2 * b];
+                G.Rfac = (float)(2.0 * mu * mu * (1.0 + mu * mu) * tran);
+                double rb = F("geom_rbound")[g];
+                G.tol2 = (float)(0.09 * rb * rb);
+                G.vert0 = v0; G.nvert = vn;
+                G.edge0 = I("mesh_edgeadr")[me];
+                G.level = lev;
+            }
+        }
+        c.glev[l][QG_NLINK + 1] = n;
+        c.ngeom[l] = n;
+    }
+#undef BADMODEL
+#undef CHECK_LEN
+    *out = m;
+    return QG_OK;
+}
+
+extern "C" void qg_model_destroy(qg_model* m) { delete m; }
+
+extern "C" int qg_model_info(const qg_model* m, int* sizes, double* timestep) {
+    if (!m) return fail(QG_EINVAL, "model is NULL");
+    if (sizes) memcpy(sizes, m->sizes, sizeof m->sizes);
+    if (timestep) *timestep = m->timestep;
+    return QG_OK;
+}
+
+// ------------------------------------------------------------------------------------------ batch
+static void default_opts(const qg_model* m, QgStepOpts& o) {
+    memset(&o, 0, sizeof o);
+    o.max_time = 10.0;
+    o.flip_termination = 0;
+    o.auto_reset = 0;
+    o.max_iter = m->c.max_iter;
+    o.ls_iter = m->c.ls_iter;
+    o.random_yaw = 0;
+    o.seed = 0;
+    o.env_offset = 0;
+    for (int i = 0; i < 12; ++i) o.reset_ctrl[i] = (i % 3 == 2) ? -0.5f : 0.f;  // quadruped.py:124
+    o.n_terms = 0;
+}
+
+extern "C" int qg_batch_create(const qg_model* m, int n_envs, int device, qg_batch** out) {
+    if (!m || !out || n_envs <= 0) return fail(QG_EINVAL, "bad arguments to qg_batch_create");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(QG_ECUDA, "no CUDA device available (%s); libquadgym has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count = 0");
+    if (device < 0 || device >= ndev) return fail(QG_EINVAL, "device %d out of range (%d devices)", device, ndev);
+    CUDA_OK(cudaSetDevice(device));
+    qg_batch* b = new qg_batch();
+    memset(b, 0, sizeof *b);
+    b->n = n_envs;
+    b->device = device;
+    default_opts(m, b->opts);
+    size_t nv = m->verts.size() / 4;
+    CUDA_OK(cudaMalloc(&b->d_model, sizeof(QgModelC)));
+    CUDA_OK(cudaMalloc(&b->d_verts, sizeof(float4) * (nv ? nv : 1)));
+    CUDA_OK(cudaMalloc(&b->d_vert_edge, sizeof(int) * (nv ? nv : 1)));
+    CUDA_OK(cudaMalloc(&b->d_mesh_edge, sizeof(int) * (m->mesh_edge.size() ? m->mesh_edge.size() : 1)));
+    CUDA_OK(cudaMalloc(&b->d_state, sizeof(float4) * (size_t)QG_NPLANE * n_envs));
+    CUDA_OK(cudaMalloc(&b->d_ctr, sizeof(QgCounters)));
+    CUDA_OK(cudaMemcpy(b->d_model, &m->c, sizeof(QgModelC), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(b->d_verts, m->verts.data(), sizeof(float) * m->verts.size(), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(b->d_vert_edge, m->vert_edge.data(), sizeof(int) * m->vert_edge.size(), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(b->d_mesh_edge, m->mesh_edge.data(), sizeof(int) * m->mesh_edge.size(), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemset(b->d_state, 0, sizeof(float4) * (size_t)QG_NPLANE * n_envs));
+    CUDA_OK(cudaMemset(b->d_ctr, 0, sizeof(QgCounters)));
+    b->smem = ((sizeof(QgModelC) + 15) & ~size_t(15)) + sizeof(float4) * nv;
+    CUDA_OK(cudaFuncSetAttribute(qg_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+    CUDA_OK(cudaFuncSetAttribute(qg_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+    *out = b;
+    int rc = qg_reset(b, nullptr, 0, 0, 0, nullptr);
+    if (rc) return rc;
+    CUDA_OK(cudaDeviceSynchronize());
+    return QG_OK;
+}
+
+extern "C" void qg_batch_destroy(qg_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    cudaFree(b->d_model); cudaFree(b->d_verts); cudaFree(b->d_vert_edge); cudaFree(b->d_mesh_edge);
+    cudaFree(b->d_state); cudaFree(b->d_ctr);
+    if (b->h_act) cudaFreeHost(b->h_act);
+    if (b->h_obs) cudaFreeHost(b->h_obs);
+    if (b->h_rew) cudaFreeHost(b->h_rew);
+    if (b->h_term) cudaFreeHost(b->h_term);
+    cudaFree(b->d_act); cudaFree(b->d_obs); cudaFree(b->d_rew); cudaFree(b->d_term);
+    delete b;
+}
+
+extern "C" int qg_batch_num_envs(const qg_batch* b) { return b ? b->n : 0; }
+
+extern "C" int qg_set_options(qg_batch* b, double max_time, int flip_termination, int auto_reset,
+                              int solver_iterations, int ls_iterations) {
+    if (!b) return fail(QG_EINVAL, "batch is NULL");
+    b->opts.max_time = max_time;
+    b->opts.flip_termination = flip_termination;
+    b->opts.auto_reset = auto_reset;
+    if (solver_iterations > 0) b->opts.max_iter = solver_iterations;
+    if (ls_iterations > 0) b->opts.ls_iter = ls_iterations;
+    return QG_OK;
+}
+
+extern "C" int qg_set_reward_table(qg_batch* b, int n_terms, const int* term_ids, const double* weights,
+                                   const double* params) {
+    if (!b) return fail(QG_EINVAL, "batch is NULL");
+    if (n_terms < 0 || n_terms > QG_MAX_TERMS) return fail(QG_EINVAL, "n_terms %d out of range [0, %d]", n_terms, QG_MAX_TERMS);
+    for (int i = 0; i < n_terms; ++i) {
+        if (term_ids[i] < 0 || term_ids[i] >= QG_NUM_TERMS) return fail(QG_EINVAL, "unknown reward term id %d", term_ids[i]);
+        b->opts.term_id[i] = term_ids[i];
+        b->opts.term_w[i] = weights ? weights[i] : 1.0;
+        b->opts.term_p[i] = params ? params[i] : 0.0;
+    }
+    b->opts.n_terms = n_terms;
+    return QG_OK;
+}
+
+static inline int nblocks(int n_envs) { return (4 * n_envs + QG_BLOCK - 1) / QG_BLOCK; }
+
+extern "C" int qg_reset(qg_batch* b, const uint8_t* mask_dev, uint64_t seed, int random_yaw, long long env_offset,
+                        void* stream) {
+    if (!b) return fail(QG_EINVAL, "batch is NULL");
+    CUDA_OK(cudaSetDevice(b->device));
+    b->opts.seed = seed;
+    b->opts.random_yaw = random_yaw;
+    b->opts.env_offset = env_offset;
+    qg_reset_kernel<<<nblocks(b->n), QG_BLOCK, 0, (cudaStream_t)stream>>>(b->d_model, b->d_state, b->n, mask_dev, b->opts,
+                                                                           mask_dev == nullptr ? 0 : 0);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return QG_OK;
+}
+
+template <bool DEBUG>
+static int launch_step(qg_batch* b, const float* action, int clip, int frame_skip, float* obs, float* reward, float* terms,
+                       unsigned char* terminated, float* terminal_obs, QgDebugOut dbg, cudaStream_t st) {
+    qg_step_kernel<DEBUG><<<nblocks(b->n), QG_BLOCK, b->smem, st>>>(b->d_model, b->d_verts, b->d_vert_edge, b->d_mesh_edge,
+                                                                     b->d_state, b->n, action, clip, frame_skip, obs, reward,
+                                                                     terms, terminated, terminal_obs, b->opts, b->d_ctr, dbg);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return QG_OK;
+}
+
+extern "C" int qg_step(qg_batch* b, const float* action_dev, int frame_skip, float* obs_dev, float* reward_dev,
+                       float* terms_dev, uint8_t* terminated_dev, float* terminal_obs_dev, void* stream) {
+    if (!b || !action_dev || !obs_dev || !reward_dev || !terminated_dev) return fail(QG_EINVAL, "qg_step: NULL argument");
+    if (frame_skip < 1) return fail(QG_EINVAL, "frame_skip must be >= 1");
+    CUDA_OK(cudaSetDevice(b->device));
+    QgDebugOut dbg;
+    memset(&dbg, 0, sizeof dbg);
+    return launch_step<false>(b, action_dev, 1, frame_skip, obs_dev, reward_dev, terms_dev, terminated_dev,
+                              terminal_obs_dev, dbg, (cudaStream_t)stream);
+}
+
+extern "C" int qg_step_host(qg_batch* b, const float* action_host, int frame_skip, float* obs_host, float* reward_host,
+                            uint8_t* terminated_host, void* stream) {
+    if (!b || !action_host || !obs_host || !reward_host || !terminated_host) return fail(QG_EINVAL, "qg_step_host: NULL argument");
+    if (frame_skip < 1) return fail(QG_EINVAL, "frame_skip must be >= 1");
+    CUDA_OK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = b->n;
+    if (!b->h_act) {
+        CUDA_OK(cudaMallocHost(&b->h_act, n * 12 * sizeof(float)));
+        CUDA_OK(cudaMallocHost(&b->h_obs, n * 33 * sizeof(float)));
+        CUDA_OK(cudaMallocHost(&b->h_rew, n * sizeof(float)));
+        CUDA_OK(cudaMallocHost(&b->h_term, n));
+        CUDA_OK(cudaMalloc(&b->d_act, n * 12 * sizeof(float)));
+        CUDA_OK(cudaMalloc(&b->d_obs, n * 33 * sizeof(float)));
+        CUDA_OK(cudaMalloc(&b->d_rew, n * sizeof(float)));
+        CUDA_OK(cudaMalloc(&b->d_term, n));
+    }
+    memcpy(b->h_act, action_host, n * 12 * sizeof(float));
+    CUDA_OK(cudaMemcpyAsync(b->d_act, b->h_act, n * 12 * sizeof(float), cudaMemcpyHostToDevice, st));
+    QgDebugOut dbg;
+    memset(&dbg, 0, sizeof dbg);
+    int rc = launch_step<false>(b, b->d_act, 1, frame_skip, b->d_obs, b->d_rew, nullptr, b->d_term, nullptr, dbg, st);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(b->h_obs, b->d_obs, n * 33 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(b->h_rew, b->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(b->h_term, b->d_term, n, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    memcpy(obs_host, b->h_obs, n * 33 * sizeof(float));
+    memcpy(reward_host, b->h_rew, n * sizeof(float));
+    memcpy(terminated_host, b->h_term, n);
+    return QG_OK;
+}
+
+extern "C" int qg_debug_step(qg_batch* b, const float* ctrl_dev, float* qacc_dev, float* qacc_smooth_dev,
+                             float* qfrc_bias_dev, float* M_dev, int* counts_dev, float* sensordata_dev, void* stream) {
+    if (!b || !ctrl_dev) return fail(QG_EINVAL, "qg_debug_step: NULL argument");
+    CUDA_OK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = b->n;
+    // scratch outputs the step kernel always writes
+    float* scratch = nullptr;
+    CUDA_OK(cudaMalloc(&scratch, n * (33 + 1) * sizeof(float) + n));
+    QgDebugOut dbg;
+    dbg.qacc = qacc_dev; dbg.qacc_smooth = qacc_smooth_dev; dbg.qfrc_bias = qfrc_bias_dev; dbg.M = M_dev;
+    dbg.counts = counts_dev; dbg.sensordata = sensordata_dev;
+    QgStepOpts saved = b->opts;
+    b->opts.auto_reset = 0;
+    b->opts.n_terms = 0;
+    int rc = launch_step<true>(b, ctrl_dev, 0, 1, scratch, scratch + n * 33, nullptr, (unsigned char*)(scratch + n * 34),
+                               nullptr, dbg, st);
+    b->opts = saved;
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(scratch);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(QG_ECUDA, "qg_debug_step: %s", cudaGetErrorString(e));
+    return QG_OK;
+}
+
+extern "C" int qg_get_state(qg_batch* b, float* qpos_dev, float* qvel_dev, float* act_dev, float* warm_dev,
+                            double* time_dev, float* ctrl_dev, void* stream) {
+    if (!b) return fail(QG_EINVAL, "batch is NULL");
+    CUDA_OK(cudaSetDevice(b->device));
+    qg_get_state_kernel<<<nblocks(b->n), QG_BLOCK, 0, (cudaStream_t)stream>>>(b->d_state, b->n, qpos_dev, qvel_dev, act_dev,
+                                                                               warm_dev, time_dev, ctrl_dev);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return QG_OK;
+}
+
+extern "C" int qg_set_state(qg_batch* b, const float* qpos_dev, const float* qvel_dev, const float* act_dev,
+                            const float* warm_dev, const double* time_dev, const float* ctrl_dev, void* stream) {
+    if (!b) return fail(QG_EINVAL, "batch is NULL");
+    CUDA_OK(cudaSetDevice(b->device));
+    qg_set_state_kernel<<<nblocks(b->n), QG_BLOCK, 0, (cudaStream_t)stream>>>(b->d_state, b->n, qpos_dev, qvel_dev, act_dev,
+                                                                               warm_dev, time_dev, ctrl_dev);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return QG_OK;
+}
+
+extern "C" int qg_get_counters(qg_batch* b, qg_counters* out_host, int reset, void* stream) {
+    if (!b || !out_host) return fail(QG_EINVAL, "qg_get_counters: NULL argument");
+    CUDA_OK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    static_assert(sizeof(qg_counters) == sizeof(QgCounters), "counter layouts differ");
+    CUDA_OK(cudaMemcpyAsync(out_host, b->d_ctr, sizeof(QgCounters), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    if (reset) CUDA_OK(cudaMemsetAsync(b->d_ctr, 0, sizeof(QgCounters), st));
+    return QG_OK;
+}
+
+extern "C" int qg_fp32_peak(int device, int iters, double* tflops_out) {
+    if (!tflops_out || iters < 1) return fail(QG_EINVAL, "qg_fp32_peak: bad argument");
+    CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8;
+    float* out = nullptr;
+    CUDA_OK(cudaMalloc(&out, sizeof(float) * threads * blocks));
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    qg_ffma_kernel<<<blocks, threads>>>(out, iters / 4 + 1, 0.999f, 0.001f);  // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_OK(cudaEventRecord(e0));
+        qg_ffma_kernel<<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
+        CUDA_OK(cudaEventRecord(e1));
+        CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        double flops = 2.0 * 8 * 16 * (double)iters * threads * blocks;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+        g_launches++;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops_out = best;
+    return QG_OK;
+}

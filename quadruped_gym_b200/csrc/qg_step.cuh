@@ -1,0 +1,781 @@
+// qg_step.cuh -- one physics step (mj_step restated B200-first) for ONE LEG PER LANE.
+//
+// Replaces mujoco.mj_step at /root/reference/src/envs/quadruped.py:165 for the model class of
+// /root/reference/src/models/quadruped/quadruped.xml.
+//
+// Mapping: 4 consecutive lanes (a "quad") own one environment; lane l owns leg l (3 hinge links,
+// their geoms, joint limits and contacts) and carries a replicated copy of the free-base state.
+// All dynamics are written in the BASE BODY frame "B" (origin = base position, axes = base axes):
+//   * leg kinematics, inertias and Jacobians do not depend on the base pose at all;
+//   * the generalised coordinates differ from MuJoCo's only in that the three linear base dofs are
+//     expressed in B instead of the world (a_B = R^T a_world); because damping and armature of
+//     those dofs are isotropic this is an exact change of variables for M, bias, J and the solver;
+//   * every contact is plane-vs-robot, so its Jacobian touches only the 6 base dofs and the 3 dofs
+//     of the owning leg.  M and the Newton Hessian H = M + J^T D J therefore share one "arrow"
+//     sparsity pattern: a 6x6 base block, four 6x3 couplings and four 3x3 leg blocks.  Each lane
+//     eliminates its own 3x3 block in registers; the 6x6 Schur complement is summed across the
+//     quad with two xor-shuffles per value and factorised redundantly by all four lanes.
+// No shared-memory scratch, no __syncthreads and no cross-quad communication on the step path.
+#pragma once
+#include "qg_math.cuh"
+#include "qg_model.h"
+
+struct LaneState {
+    v3 pb;                 // base position (world)
+    float qw, qx, qy, qz;  // base quaternion
+    v3 vw, om;             // base linear velocity (world), angular velocity (body)
+    v3 wl, wa;             // qacc_warmstart of the base (world lin, body ang)
+    double time;
+    float q[3], qd[3], act[3], wj[3], ctrl[3];
+};
+
+struct SensorOut {
+    float jq[3];
+    v3 acc, gyro, pos, linvel, xaxis, zaxis, vel;
+};
+
+struct StepStats {
+    int ncon, nefc, niter, nls, nvert, overflow;
+};
+
+// per-lane contact table (thread-local memory; only the first `nc` slots are ever touched)
+struct Contacts {
+    float x[QG_MAXCON_LANE], y[QG_MAXCON_LANE], z[QG_MAXCON_LANE];
+    float D[QG_MAXCON_LANE], mu[QG_MAXCON_LANE], Bd[QG_MAXCON_LANE], Kr[QG_MAXCON_LANE];
+    float jar[4][QG_MAXCON_LANE], jv[4][QG_MAXCON_LANE];
+    int lev[QG_MAXCON_LANE];
+    int n;
+};
+
+DI float impedance(float r, float d0, float dmax, float width, float mid, float power) {
+    float x = fabsf(r) / fmaxf(1e-15f, width), y;
+    if (x >= 1.f) y = 1.f;
+    else if (x <= 0.f) y = 0.f;
+    else if (power == 2.f) y = (x <= mid) ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
+    else if (power == 1.f) y = x;
+    else y = (x <= mid) ? powf(x / mid, power) * mid : 1.f - powf((1.f - x) / (1.f - mid), power) * (1.f - mid);
+    float v = fmaf(y, dmax - d0, d0);
+    return fminf(fmaxf(v, 1e-4f), 0.9999f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// plane-vs-hull collision of the geoms this lane owns at one tree level (mjc_PlaneConvex restated)
+DI void collide_level(const QgModelC& P, const float4* __restrict__ verts, const int* __restrict__ vert_edge,
+                      const int* __restrict__ mesh_edge, int leg, int g0, int g1, int level,
+                      v3 pk, const m3& Rk, v3 up, float zb, Contacts& C, StepStats& st) {
+    for (int g = g0; g < g1; ++g) {
+        const QgGeomC& G = P.geom[leg][g];
+        v3 ctr = pk + mul(Rk, ld3(G.pos));
+        float zc = zb + dot(up, ctr);
+        m3 RB = matmul(Rk, ldm3(G.R));  // mesh frame -> B
+        v3 dl = tmul(RB, up);           // "up" in the mesh frame
+        float ext = fmaf(fabsf(dl.x), G.half[0], fmaf(fabsf(dl.y), G.half[1], fabsf(dl.z) * G.half[2]));
+        float margin = G.margin;
+        if (zc - ext > margin) continue;  // oriented-box cull (conservative; same contacts as any cull)
+        const float4* __restrict__ vt = verts + G.vert0;
+        int nvert = G.nvert, best = 0;
+        float hbest = 3.0e38f;
+        for (int i = 0; i < nvert; ++i) {
+            float4 v = vt[i];
+            float h = fmaf(dl.x, v.x, fmaf(dl.y, v.y, dl.z * v.z));
+            if (h < hbest) { hbest = h; best = i; }
+        }
+        st.nvert += nvert;
+        if (zc + hbest > margin) continue;
+        // support vertex first, then its hull-graph neighbours (up to 4 contacts per geom)
+        const int* __restrict__ e = mesh_edge + G.edge0 + __ldg(vert_edge + G.vert0 + best);
+        int cnt = 0, cand = best;
+        v3 prev0 = V3(0, 0, 0), prev1 = prev0, prev2 = prev0;
+        for (;;) {
+            float4 v = vt[cand];
+            v3 xv = ctr + mul(RB, V3(v.x, v.y, v.z));
+            float dv = zb + dot(up, xv);
+            bool ok = (cnt == 0) || (dv <= margin);
+            if (ok && cnt > 0) {
+                v3 e0 = xv - prev0, e1 = xv - prev1, e2 = xv - prev2;
+                if (dot(e0, e0) < G.tol2) ok = false;
+                if (!P.rule_first) {
+                    if (cnt > 1 && dot(e1, e1) < G.tol2) ok = false;
+                    if (cnt > 2 && dot(e2, e2) < G.tol2) ok = false;
+                }
+            }
+            if (ok) {
+                if (cnt == 0) prev0 = xv; else if (cnt == 1) prev1 = xv; else if (cnt == 2) prev2 = xv;
+                cnt++;
+                if (dv < margin) {  // includemargin: rows are instantiated only for dist < margin
+                    if (C.n < QG_MAXCON_LANE) {
+                        int c = C.n++;
+                        v3 xc = fma3(-0.5f * dv, up, xv);
+                        float r = dv - margin;
+                        float imp = impedance(r, G.d0, G.dmax, G.width, G.mid, G.power);
+                        C.x[c] = xc.x; C.y[c] = xc.y; C.z[c] = xc.z;
+                        C.D[c] = 1.f / fmaxf(1e-15f, (1.f - imp) / imp * G.Rfac);
+                        C.mu[c] = G.mu;
+                        C.Bd[c] = G.B;
+                        C.Kr[c] = G.K * imp * r;
+                        C.lev[c] = level;
+                    } else st.overflow++;
+                }
+            }
+            if (cnt >= 4) break;
+            int nb = __ldg(e++);
+            if (nb < 0) break;
+            cand = nb;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// arrow-structured SPD solve  [Abb Abl; Alb All] [xb; xl] = [rb; rl]
+//   All (3x3 sym: 00 01 02 11 12 22) and Abl (6x3, [r*3+c]) are lane-local,
+//   Abb = Acommon (identical on the 4 lanes) + sum over lanes of Alocal (may be NULL),
+//   rb is identical on all lanes.
+DI void arrow_solve(const float* All, const float* Abl, const float* Alocal, const float* Acommon,
+                    const float* rb, const float* rl, unsigned qm, float* xb, float* xl) {
+    // LDL^T of the leg block
+    float d0 = fmaxf(All[0], 1e-12f), i0 = 1.f / d0;
+    float l10 = All[1] * i0, l20 = All[2] * i0;
+    float d1 = fmaxf(All[3] - l10 * All[1], 1e-12f), i1 = 1.f / d1;
+    float l21 = (All[4] - l20 * All[1]) * i1;
+    float d2 = fmaxf(All[5] - l20 * All[2] - l21 * (All[4] - l20 * All[1]), 1e-12f), i2 = 1.f / d2;
+#define LEG_SOLVE(b0, b1, b2, o0, o1, o2)            \
+    {                                                 \
+        float y0 = (b0), y1 = (b1)-l10 * y0;          \
+        float y2 = (b2)-l20 * y0 - l21 * y1;          \
+        o2 = y2 * i2;                                 \
+        o1 = y1 * i1 - l21 * o2;                      \
+        o0 = y0 * i0 - l10 * o1 - l20 * o2;           \
+    }
+    float Y[18];  // Y[r*3+c] = (All^-1 Abl[r,:]^T)[c]
+#pragma unroll
+    for (int r = 0; r < 6; ++r) LEG_SOLVE(Abl[r * 3], Abl[r * 3 + 1], Abl[r * 3 + 2], Y[r * 3], Y[r * 3 + 1], Y[r * 3 + 2]);
+    float t0, t1, t2;
+    LEG_SOLVE(rl[0], rl[1], rl[2], t0, t1, t2);
+    float A[21], b[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            float s = fmaf(Abl[i * 3], Y[j * 3], fmaf(Abl[i * 3 + 1], Y[j * 3 + 1], Abl[i * 3 + 2] * Y[j * 3 + 2]));
+            float loc = Alocal ? Alocal[IX6(i, j)] - s : -s;
+            A[IX6(i, j)] = Acommon[IX6(i, j)] + qsum(loc, qm);
+        }
+        float sb = fmaf(Abl[i * 3], t0, fmaf(Abl[i * 3 + 1], t1, Abl[i * 3 + 2] * t2));
+        b[i] = rb[i] - qsum(sb, qm);
+    }
+    // dense Cholesky of the 6x6 Schur complement (redundant on the 4 lanes, identical bits)
+    float inv[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        float s = A[IX6(j, j)];
+#pragma unroll
+        for (int k = 0; k < j; ++k) s -= A[IX6(j, k)] * A[IX6(j, k)];
+        s = sqrtf(fmaxf(s, 1e-12f));
+        inv[j] = 1.f / s;
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+            float t = A[IX6(i, j)];
+#pragma unroll
+            for (int k = 0; k < j; ++k) t -= A[IX6(i, k)] * A[IX6(j, k)];
+            A[IX6(i, j)] = t * inv[j];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        float s = b[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) s -= A[IX6(i, k)] * b[k];
+        b[i] = s * inv[i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        float s = b[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; ++k) s -= A[IX6(k, i)] * xb[k];
+        xb[i] = s * inv[i];
+    }
+    float x0 = t0, x1 = t1, x2 = t2;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        x0 -= Y[r * 3] * xb[r];
+        x1 -= Y[r * 3 + 1] * xb[r];
+        x2 -= Y[r * 3 + 2] * xb[r];
+    }
+    xl[0] = x0; xl[1] = x1; xl[2] = x2;
+#undef LEG_SOLVE
+}
+
+// y = M x on the arrow pattern
+DI void arrow_matvec(const float* Mll, const float* Mbl, const float* Mbb, const float* xb, const float* xl,
+                     unsigned qm, float* yb, float* yl) {
+    yl[0] = fmaf(Mll[0], xl[0], fmaf(Mll[1], xl[1], Mll[2] * xl[2]));
+    yl[1] = fmaf(Mll[1], xl[0], fmaf(Mll[3], xl[1], Mll[4] * xl[2]));
+    yl[2] = fmaf(Mll[2], xl[0], fmaf(Mll[4], xl[1], Mll[5] * xl[2]));
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        yl[0] = fmaf(Mbl[r * 3], xb[r], yl[0]);
+        yl[1] = fmaf(Mbl[r * 3 + 1], xb[r], yl[1]);
+        yl[2] = fmaf(Mbl[r * 3 + 2], xb[r], yl[2]);
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        float s = fmaf(Mbl[r * 3], xl[0], fmaf(Mbl[r * 3 + 1], xl[1], Mbl[r * 3 + 2] * xl[2]));
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) t = fmaf(Mbb[r >= k ? IX6(r, k) : IX6(k, r)], xb[k], t);
+        yb[r] = t + qsum(s, qm);
+    }
+}
+
+// spatial velocity prefixes of a generalised vector: U[k] + W[k] x p = velocity of a point p on link k
+DI void twist(const float* xb, const float* xl, const v3* sl, const v3* sa, v3* U, v3* W) {
+    U[0] = V3(xb[0], xb[1], xb[2]);
+    W[0] = V3(xb[3], xb[4], xb[5]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        U[j + 1] = fma3(xl[j], sl[j], U[j]);
+        W[j + 1] = fma3(xl[j], sa[j], W[j]);
+    }
+}
+DI v3 sel4(const v3* A, int lev) { return lev == 0 ? A[0] : (lev == 1 ? A[1] : (lev == 2 ? A[2] : A[3])); }
+
+// rows of the 4-sided friction pyramid for a point velocity u: n + mu t1, n - mu t1, n + mu t2, n - mu t2
+// with n = +z, t1 = +y, t2 = -x of the world (rows of the base rotation in B coordinates)
+DI void pyramid_rows(v3 u, v3 tx, v3 ty, v3 up, float mu, float* r) {
+    float un = dot(up, u), u1 = mu * dot(ty, u), u2 = -mu * dot(tx, u);
+    r[0] = un + u1; r[1] = un - u1; r[2] = un + u2; r[3] = un - u2;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <bool DEBUG>
+DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const int* __restrict__ vert_edge,
+                     const int* __restrict__ mesh_edge, LaneState& S, int leg, unsigned qm,
+                     int max_iter, int ls_iter, bool want_sensors, SensorOut& so, StepStats& st, Contacts& C,
+                     const QgDebugOut& dbg, int env) {
+    const float h = P.timestep;
+    // ---- base frame
+    float qn = 1.f / sqrtf(S.qw * S.qw + S.qx * S.qx + S.qy * S.qy + S.qz * S.qz);
+    float w = S.qw * qn, x = S.qx * qn, y = S.qy * qn, z = S.qz * qn;
+    m3 Rb;  // world <- B
+    Rb.r0 = V3(1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y));
+    Rb.r1 = V3(2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x));
+    Rb.r2 = V3(2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y));
+    const v3 tx = Rb.r0, ty = Rb.r1, up = Rb.r2;  // world axes in B coordinates
+    const v3 vB = tmul(Rb, S.vw);
+    const v3 gB = tmul(Rb, ld3(P.grav));
+    const float zb = S.pb.z - P.plane_z;
+
+    // ---- leg chain: kinematics, collision, inertias, velocity recursion (all in B)
+    C.n = 0;
+    m3 Rk;
+    Rk.r0 = V3(1, 0, 0); Rk.r1 = V3(0, 1, 0); Rk.r2 = V3(0, 0, 1);
+    v3 pk = V3(0, 0, 0);
+    collide_level(P, verts, vert_edge, mesh_edge, leg, 0, P.glev[leg][1], 0, pk, Rk, up, zb, C, st);
+
+    v3 sl[3], sa[3];        // joint spatial motion about the B origin: linear p x a, angular a
+    v3 ck[3];               // link CoM
+    s3 Ik[3];               // link inertia about its CoM, B axes
+    v3 Fk[3], Nk[3];        // RNE: inertial force and moment about the B origin
+    v3 omk = S.om, alk = V3(0, 0, 0), apk = -gB;  // angular velocity / acceleration, origin acceleration
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const QgJointC& J = P.joint[leg][k];
+        v3 pn = pk + mul(Rk, ld3(J.pos));
+        m3 Rp = matmul(Rk, ldm3(J.Roff));
+        float sn, cs;
+        sincosf(S.q[k] - J.q0, &sn, &cs);
+        m3 Rn;  // Rp * Rz(theta)
+        Rn.r0 = V3(cs * Rp.r0.x + sn * Rp.r0.y, cs * Rp.r0.y - sn * Rp.r0.x, Rp.r0.z);
+        Rn.r1 = V3(cs * Rp.r1.x + sn * Rp.r1.y, cs * Rp.r1.y - sn * Rp.r1.x, Rp.r1.z);
+        Rn.r2 = V3(cs * Rp.r2.x + sn * Rp.r2.y, cs * Rp.r2.y - sn * Rp.r2.x, Rp.r2.z);
+        v3 a = col2(Rn);
+        // velocity recursion (classical accelerations, zero generalised acceleration, gravity as base accel)
+        v3 r = pn - pk;
+        apk = apk + cross(alk, r) + cross(omk, cross(omk, r));
+        v3 aq = S.qd[k] * a;
+        alk = alk + cross(omk, aq);
+        omk = omk + aq;
+        pk = pn;
+        Rk = Rn;
+        sa[k] = a;
+        sl[k] = cross(pk, a);
+        v3 dcm = mul(Rk, ld3(J.com));
+        ck[k] = pk + dcm;
+        s3 Ib;
+        Ib.xx = J.I[0]; Ib.yy = J.I[1]; Ib.zz = J.I[2]; Ib.xy = J.I[3]; Ib.xz = J.I[4]; Ib.yz = J.I[5];
+        Ik[k] = rot_sym(Rk, Ib);
+        v3 ac = apk + cross(alk, dcm) + cross(omk, cross(omk, dcm));
+        Fk[k] = J.mass * ac;
+        Nk[k] = mul(Ik[k], alk) + cross(omk, mul(Ik[k], omk)) + cross(ck[k], Fk[k]);
+        collide_level(P, verts, vert_edge, mesh_edge, leg, P.glev[leg][k + 1], P.glev[leg][k + 2], k + 1, pk, Rk, up, zb, C, st);
+    }
+
+    // ---- backward pass: composite inertias -> M blocks, RNE forces -> bias
+    float Mll[6], Mbl[18], Mbb[21];
+    float bias_l[3];
+    v3 fsum = V3(0, 0, 0), nsum = V3(0, 0, 0);
+    float cm = 0.f;
+    v3 chv = V3(0, 0, 0);
+    s3 cI;
+    cI.xx = cI.yy = cI.zz = cI.xy = cI.xz = cI.yz = 0.f;
+#pragma unroll
+    for (int k = 2; k >= 0; --k) {
+        const QgJointC& J = P.joint[leg][k];
+        float m = J.mass;
+        v3 c = ck[k];
+        float c2 = dot(c, c);
+        cm += m;
+        chv = fma3(m, c, chv);
+        cI.xx += Ik[k].xx + m * (c2 - c.x * c.x);
+        cI.yy += Ik[k].yy + m * (c2 - c.y * c.y);
+        cI.zz += Ik[k].zz + m * (c2 - c.z * c.z);
+        cI.xy += Ik[k].xy - m * c.x * c.y;
+        cI.xz += Ik[k].xz - m * c.x * c.z;
+        cI.yz += Ik[k].yz - m * c.y * c.z;
+        v3 pl = fma3(cm, sl[k], cross(sa[k], chv));     // linear momentum per unit joint rate
+        v3 Lo = mul(cI, sa[k]) + cross(chv, sl[k]);     // angular momentum about the B origin
+        Mbl[0 * 3 + k] = pl.x; Mbl[1 * 3 + k] = pl.y; Mbl[2 * 3 + k] = pl.z;
+        Mbl[3 * 3 + k] = Lo.x; Mbl[4 * 3 + k] = Lo.y; Mbl[5 * 3 + k] = Lo.z;
+#pragma unroll
+        for (int i = 0; i <= k; ++i) {
+            float v = dot(sl[i], pl) + dot(sa[i], Lo);
+            int idx = (i == 0) ? k : (i == 1 ? 2 + k : 5);  // (0,k)->0,1,2  (1,k)->3,4  (2,2)->5
+            Mll[idx] = v + ((i == k) ? J.armature : 0.f);
+        }
+        fsum += Fk[k];
+        nsum += Nk[k];
+        bias_l[k] = dot(sl[k], fsum) + dot(sa[k], nsum);
+    }
+    // base: own body + legs (quad sums)
+    {
+        v3 c0 = ld3(P.base_com);
+        float m0 = P.base_mass;
+        v3 ac0 = -gB + cross(S.om, cross(S.om, c0));
+        v3 F0 = m0 * ac0;
+        s3 I0;
+        I0.xx = P.base_I[0]; I0.yy = P.base_I[1]; I0.zz = P.base_I[2];
+        I0.xy = P.base_I[3]; I0.xz = P.base_I[4]; I0.yz = P.base_I[5];
+        v3 N0 = cross(S.om, mul(I0, S.om)) + cross(c0, F0);
+        fsum = qsum(fsum, qm) + F0;
+        nsum = qsum(nsum, qm) + N0;
+        float mt = qsum(cm, qm) + m0;
+        v3 ht = qsum(chv, qm) + m0 * c0;
+        float c2 = dot(c0, c0);
+        s3 It;
+        It.xx = qsum(cI.xx, qm) + I0.xx + m0 * (c2 - c0.x * c0.x);
+        It.yy = qsum(cI.yy, qm) + I0.yy + m0 * (c2 - c0.y * c0.y);
+        It.zz = qsum(cI.zz, qm) + I0.zz + m0 * (c2 - c0.z * c0.z);
+        It.xy = qsum(cI.xy, qm) + I0.xy - m0 * c0.x * c0.y;
+        It.xz = qsum(cI.xz, qm) + I0.xz - m0 * c0.x * c0.z;
+        It.yz = qsum(cI.yz, qm) + I0.yz - m0 * c0.y * c0.z;
+#pragma unroll
+        for (int i = 0; i < 21; ++i) Mbb[i] = 0.f;
+        Mbb[IX6(0, 0)] = mt + P.base_arm[0]; Mbb[IX6(1, 1)] = mt + P.base_arm[1]; Mbb[IX6(2, 2)] = mt + P.base_arm[2];
+        // angular rows x linear cols = [h]x
+        Mbb[IX6(3, 1)] = -ht.z; Mbb[IX6(3, 2)] = ht.y;
+        Mbb[IX6(4, 0)] = ht.z;  Mbb[IX6(4, 2)] = -ht.x;
+        Mbb[IX6(5, 0)] = -ht.y; Mbb[IX6(5, 1)] = ht.x;
+        Mbb[IX6(3, 3)] = It.xx + P.base_arm[3]; Mbb[IX6(4, 4)] = It.yy + P.base_arm[4]; Mbb[IX6(5, 5)] = It.zz + P.base_arm[5];
+        Mbb[IX6(4, 3)] = It.xy; Mbb[IX6(5, 3)] = It.xz; Mbb[IX6(5, 4)] = It.yz;
+    }
+
+    // ---- passive + actuation -> qfrc_smooth (B form)
+    float fsb[6], fsl[3], act_dot[3], dimp[3];  // dimp: implicit-integrator diagonal (damping + servo kv)
+    fsb[0] = -P.base_damp[0] * vB.x - fsum.x; fsb[1] = -P.base_damp[1] * vB.y - fsum.y; fsb[2] = -P.base_damp[2] * vB.z - fsum.z;
+    fsb[3] = -P.base_damp[3] * S.om.x - nsum.x; fsb[4] = -P.base_damp[4] * S.om.y - nsum.y; fsb[5] = -P.base_damp[5] * S.om.z - nsum.z;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const QgJointC& J = P.joint[leg][k];
+        float tau = 0.f;
+        act_dot[k] = 0.f;
+        dimp[k] = J.damping;
+        if (J.has_act) {
+            float c = S.ctrl[k];
+            if (J.ctrl_limited) c = fminf(fmaxf(c, J.ctrl_lo), J.ctrl_hi);
+            float ain = c;
+            if (J.has_dyn) { act_dot[k] = (c - S.act[k]) * J.inv_tau; ain = S.act[k]; }
+            float f = fmaf(J.kp, ain, J.b0) + J.b1 * (J.gear * S.q[k]) + J.b2 * (J.gear * S.qd[k]);
+            bool clamped = false;
+            if (J.frc_limited) {
+                if (f <= J.frc_lo) { f = J.frc_lo; clamped = true; }
+                else if (f >= J.frc_hi) { f = J.frc_hi; clamped = true; }
+            }
+            tau = J.gear * f;
+            if (!clamped && P.integrator == 1) dimp[k] -= J.gear * J.gear * J.b2;
+        }
+        fsl[k] = -J.damping * S.qd[k] - bias_l[k] + tau;
+    }
+
+    // ---- unconstrained acceleration
+    float a0b[6], a0l[3];
+    arrow_solve(Mll, Mbl, nullptr, Mbb, fsb, fsl, qm, a0b, a0l);
+
+    // ---- constraint rows: joint limits (own dofs) and pyramidal contacts (table C)
+    float lsgn[3], lD[3], ljar[3], ljv[3];
+    int nlim = 0;
+    float qdb[6] = {vB.x, vB.y, vB.z, S.om.x, S.om.y, S.om.z};
+    v3 U[4], W[4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const QgJointC& J = P.joint[leg][k];
+        lsgn[k] = 0.f; lD[k] = 0.f; ljar[k] = 0.f; ljv[k] = 0.f;
+        if (J.limited) {
+            float dlo = S.q[k] - J.lo, dhi = J.hi - S.q[k];
+            float dist = 0.f, sg = 0.f;
+            if (dlo < 0.f) { dist = dlo; sg = 1.f; }
+            else if (dhi < 0.f) { dist = dhi; sg = -1.f; }
+            if (sg != 0.f) {
+                float imp = impedance(dist, P.lim_d0, P.lim_dmax, P.lim_width, P.lim_mid, P.lim_power);
+                lsgn[k] = sg;
+                lD[k] = 1.f / fmaxf(1e-15f, (1.f - imp) / imp * J.invw_dof);
+                ljar[k] = P.lim_B * (sg * S.qd[k]) + P.lim_K * imp * dist;  // = -aref
+                nlim++;
+            }
+        }
+    }
+    const int nc = C.n;
+    twist(qdb, S.qd, sl, sa, U, W);
+    for (int c = 0; c < nc; ++c) {
+        v3 xc = V3(C.x[c], C.y[c], C.z[c]);
+        int lev = C.lev[c];
+        float rv[4];
+        pyramid_rows(sel4(U, lev) + cross(sel4(W, lev), xc), tx, ty, up, C.mu[c], rv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) C.jar[k][c] = fmaf(C.Bd[c], rv[k], C.Kr[c]);  // = -aref_k
+    }
+    const int nefc = qsumi(4 * nc + nlim, qm);
+    st.ncon += nc;
+    st.nefc += 4 * nc + nlim;
+
+    float ab[6], al[3];       // solver acceleration (B form)
+    float fcb[6], fcl[3];     // constraint force J^T f
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { ab[i] = a0b[i]; fcb[i] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { al[i] = a0l[i]; fcl[i] = 0.f; }
+
+    if (nefc > 0) {
+        float Mab[6], Mal[3];
+        // -- warm start: compare the cost at qacc_warmstart and at qacc_smooth
+        {
+            v3 wlB = tmul(Rb, S.wl);
+            float wb[6] = {wlB.x, wlB.y, wlB.z, S.wa.x, S.wa.y, S.wa.z};
+            float cw = 0.f, cs = 0.f;
+            v3 U2[4], W2[4];
+            twist(wb, S.wj, sl, sa, U, W);
+            twist(a0b, a0l, sl, sa, U2, W2);
+            for (int c = 0; c < nc; ++c) {
+                v3 xc = V3(C.x[c], C.y[c], C.z[c]);
+                int lev = C.lev[c];
+                float rw[4], rs[4], D = C.D[c];
+                pyramid_rows(sel4(U, lev) + cross(sel4(W, lev), xc), tx, ty, up, C.mu[c], rw);
+                pyramid_rows(sel4(U2, lev) + cross(sel4(W2, lev), xc), tx, ty, up, C.mu[c], rs);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float base = C.jar[k][c];
+                    float jw = rw[k] + base, js = rs[k] + base;
+                    C.jar[k][c] = jw;
+                    C.jv[k][c] = js;
+                    cw += (jw < 0.f) ? 0.5f * D * jw * jw : 0.f;
+                    cs += (js < 0.f) ? 0.5f * D * js * js : 0.f;
+                }
+            }
+            float ljs[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float jw = fmaf(lsgn[k], S.wj[k], ljar[k]), js = fmaf(lsgn[k], a0l[k], ljar[k]);
+                ljs[k] = js;
+                ljar[k] = jw;
+                cw += (lsgn[k] != 0.f && jw < 0.f) ? 0.5f * lD[k] * jw * jw : 0.f;
+                cs += (lsgn[k] != 0.f && js < 0.f) ? 0.5f * lD[k] * js * js : 0.f;
+            }
+            arrow_matvec(Mll, Mbl, Mbb, wb, S.wj, qm, Mab, Mal);
+            float gl = 0.f, gb = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) gl += 0.5f * (Mal[k] - fsl[k]) * (S.wj[k] - a0l[k]);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) gb += 0.5f * (Mab[r] - fsb[r]) * (wb[r] - a0b[r]);
+            float cost_w = qsum(cw + gl, qm) + gb, cost_s = qsum(cs, qm);
+            if (cost_w < cost_s) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) ab[i] = wb[i];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) al[i] = S.wj[i];
+            } else {
+                for (int c = 0; c < nc; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) C.jar[k][c] = C.jv[k][c];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { ljar[k] = ljs[k]; Mal[k] = fsl[k]; }
+#pragma unroll
+                for (int r = 0; r < 6; ++r) Mab[r] = fsb[r];
+            }
+        }
+
+        // -- primal Newton iterations
+        float cost_old = 0.f;
+        int iter = 0;
+        for (;;) {
+            float Hll[6], Hbl[18], Hc[21];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) Hll[i] = Mll[i];
+#pragma unroll
+            for (int i = 0; i < 18; ++i) Hbl[i] = Mbl[i];
+#pragma unroll
+            for (int i = 0; i < 21; ++i) Hc[i] = 0.f;
+            float cost = 0.f;
+            v3 Fb = V3(0, 0, 0), Nb = V3(0, 0, 0);
+            float tau[3] = {0.f, 0.f, 0.f};
+            for (int c = 0; c < nc; ++c) {
+                float D = C.D[c], mu = C.mu[c];
+                float j0 = C.jar[0][c], j1 = C.jar[1][c], j2 = C.jar[2][c], j3 = C.jar[3][c];
+                float a0 = j0 < 0.f ? 1.f : 0.f, a1 = j1 < 0.f ? 1.f : 0.f, a2 = j2 < 0.f ? 1.f : 0.f, a3 = j3 < 0.f ? 1.f : 0.f;
+                float na = a0 + a1 + a2 + a3;
+                if (na == 0.f) continue;
+                float f0 = -D * a0 * j0, f1 = -D * a1 * j1, f2 = -D * a2 * j2, f3 = -D * a3 * j3;
+                cost += 0.5f * D * (a0 * j0 * j0 + a1 * j1 * j1 + a2 * j2 * j2 + a3 * j3 * j3);
+                v3 xc = V3(C.x[c], C.y[c], C.z[c]);
+                int lev = C.lev[c];
+                // force vector in B: sum f_k w_k,  w = up +- mu*ty, up -+ mu*tx
+                v3 fc = fma3(f0 + f1 + f2 + f3, up, fma3(mu * (f0 - f1), ty, (-mu * (f2 - f3)) * tx));
+                v3 nn = cross(xc, fc);
+                Fb += fc;
+                Nb += nn;
+                // Jacobian columns of the leg joints at the contact point (zero above the contact's link)
+                v3 jc0 = lev >= 1 ? sl[0] + cross(sa[0], xc) : V3(0, 0, 0);
+                v3 jc1 = lev >= 2 ? sl[1] + cross(sa[1], xc) : V3(0, 0, 0);
+                v3 jc2 = lev >= 3 ? sl[2] + cross(sa[2], xc) : V3(0, 0, 0);
+                tau[0] += dot(jc0, fc); tau[1] += dot(jc1, fc); tau[2] += dot(jc2, fc);
+                // W = D * sum_active w w^T  in the (tx, ty, up) basis: diag/offdiag coefficients
+                float sy = a0 + a1, sx = a2 + a3;     // rows touching ty / tx
+                float dy = a0 - a1, dx = a3 - a2;     // signed: w0=up+mu ty, w1=up-mu ty, w2=up-mu tx, w3=up+mu tx
+                float wuu = D * na, wyy = D * mu * mu * sy, wxx = D * mu * mu * sx, wuy = D * mu * dy, wux = D * mu * dx;
+                // W v = wuu up(up.v) + wyy ty(ty.v) + wxx tx(tx.v) + wuy (up(ty.v)+ty(up.v)) + wux (up(tx.v)+tx(up.v))
+#define WMUL(v, out)                                                                                   \
+    {                                                                                                  \
+        float pu = dot(up, v), py = dot(ty, v), px = dot(tx, v);                                       \
+        out = fma3(wuu * pu + wuy * py + wux * px, up, fma3(wyy * py + wuy * pu, ty, (wxx * px + wux * pu) * tx)); \
+    }
+                v3 Wx, Wy, Wz, q0, q1, q2;
+                WMUL(V3(1, 0, 0), Wx);
+                WMUL(V3(0, 1, 0), Wy);
+                WMUL(V3(0, 0, 1), Wz);
+                WMUL(jc0, q0);
+                WMUL(jc1, q1);
+                WMUL(jc2, q2);
+#undef WMUL
+                Hll[0] += dot(jc0, q0); Hll[1] += dot(jc0, q1); Hll[2] += dot(jc0, q2);
+                Hll[3] += dot(jc1, q1); Hll[4] += dot(jc1, q2); Hll[5] += dot(jc2, q2);
+                v3 x0 = cross(xc, q0), x1 = cross(xc, q1), x2 = cross(xc, q2);
+                Hbl[0] += q0.x; Hbl[1] += q1.x; Hbl[2] += q2.x;
+                Hbl[3] += q0.y; Hbl[4] += q1.y; Hbl[5] += q2.y;
+                Hbl[6] += q0.z; Hbl[7] += q1.z; Hbl[8] += q2.z;
+                Hbl[9] += x0.x; Hbl[10] += x1.x; Hbl[11] += x2.x;
+                Hbl[12] += x0.y; Hbl[13] += x1.y; Hbl[14] += x2.y;
+                Hbl[15] += x0.z; Hbl[16] += x1.z; Hbl[17] += x2.z;
+                // base block  [[W, -W X], [X W, -X W X]]
+                Hc[IX6(0, 0)] += Wx.x; Hc[IX6(1, 0)] += Wy.x; Hc[IX6(1, 1)] += Wy.y;
+                Hc[IX6(2, 0)] += Wz.x; Hc[IX6(2, 1)] += Wz.y; Hc[IX6(2, 2)] += Wz.z;
+                v3 A0 = cross(xc, Wx), A1 = cross(xc, Wy), A2 = cross(xc, Wz);  // columns of X W
+                Hc[IX6(3, 0)] += A0.x; Hc[IX6(3, 1)] += A1.x; Hc[IX6(3, 2)] += A2.x;
+                Hc[IX6(4, 0)] += A0.y; Hc[IX6(4, 1)] += A1.y; Hc[IX6(4, 2)] += A2.y;
+                Hc[IX6(5, 0)] += A0.z; Hc[IX6(5, 1)] += A1.z; Hc[IX6(5, 2)] += A2.z;
+                // -X W X : row i = cross(xc, row_i(XW)),  row_i(XW) = (A0[i], A1[i], A2[i])
+                v3 r3 = cross(xc, V3(A0.x, A1.x, A2.x)), r4 = cross(xc, V3(A0.y, A1.y, A2.y)), r5 = cross(xc, V3(A0.z, A1.z, A2.z));
+                Hc[IX6(3, 3)] += r3.x; Hc[IX6(4, 3)] += r4.x; Hc[IX6(4, 4)] += r4.y;
+                Hc[IX6(5, 3)] += r5.x; Hc[IX6(5, 4)] += r5.y; Hc[IX6(5, 5)] += r5.z;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (lsgn[k] != 0.f && ljar[k] < 0.f) {
+                    float f = -lD[k] * ljar[k];
+                    cost += 0.5f * lD[k] * ljar[k] * ljar[k];
+                    tau[k] += lsgn[k] * f;
+                    Hll[k == 0 ? 0 : (k == 1 ? 3 : 5)] += lD[k];
+                }
+            }
+            float gauss_l = 0.f, gauss_b = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) gauss_l += 0.5f * (Mal[k] - fsl[k]) * (al[k] - a0l[k]);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) gauss_b += 0.5f * (Mab[r] - fsb[r]) * (ab[r] - a0b[r]);
+            cost = qsum(cost + gauss_l, qm) + gauss_b;
+            Fb = qsum(Fb, qm);
+            Nb = qsum(Nb, qm);
+            fcb[0] = Fb.x; fcb[1] = Fb.y; fcb[2] = Fb.z; fcb[3] = Nb.x; fcb[4] = Nb.y; fcb[5] = Nb.z;
+            float gb[6], gl[3], g2 = 0.f, g2b = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { fcl[k] = tau[k]; gl[k] = Mal[k] - fsl[k] - tau[k]; g2 += gl[k] * gl[k]; }
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { gb[r] = Mab[r] - fsb[r] - fcb[r]; g2b += gb[r] * gb[r]; }
+            if (iter > 0) {
+                float gradient = P.scale * sqrtf(qsum(g2, qm) + g2b);
+                float improvement = P.scale * (cost_old - cost);
+                if (improvement < P.tol || gradient < P.tol || iter >= max_iter) break;
+            }
+            // Newton direction
+            float sb[6], sv[3], nb6[6], nl3[3];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) nb6[r] = -gb[r];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) nl3[k] = -gl[k];
+            arrow_solve(Hll, Hbl, Hc, Mbb, nb6, nl3, qm, sb, sv);
+            float Mvb[6], Mvl[3];
+            arrow_matvec(Mll, Mbl, Mbb, sb, sv, qm, Mvb, Mvl);
+            float q1l = 0.f, q2l = 0.f, q1b = 0.f, q2b = 0.f, snl = 0.f, snb = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { q1l += sv[k] * (Mal[k] - fsl[k]); q2l += 0.5f * sv[k] * Mvl[k]; snl += sv[k] * sv[k]; }
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { q1b += sb[r] * (Mab[r] - fsb[r]); q2b += 0.5f * sb[r] * Mvb[r]; snb += sb[r] * sb[r]; }
+            float q1 = qsum(q1l, qm) + q1b, q2 = qsum(q2l, qm) + q2b, snorm = sqrtf(qsum(snl, qm) + snb);
+            if (snorm < 1e-15f) break;
+            twist(sb, sv, sl, sa, U, W);
+            for (int c = 0; c < nc; ++c) {
+                v3 xc = V3(C.x[c], C.y[c], C.z[c]);
+                int lev = C.lev[c];
+                float rv[4];
+                pyramid_rows(sel4(U, lev) + cross(sel4(W, lev), xc), tx, ty, up, C.mu[c], rv);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) C.jv[k][c] = rv[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) ljv[k] = lsgn[k] * sv[k];
+            // exact line search on the convex piecewise-quadratic: safeguarded Newton on the derivative
+            float alpha = 0.f, lo = 0.f, hi = -1.f, d1 = 0.f, d2 = 0.f;
+            float gtol = fmaxf(P.tol * 0.01f * snorm / P.scale, 1e-6f * fabsf(q1));
+            for (int it = 0; it <= ls_iter; ++it) {
+                float e1 = 0.f, e2 = 0.f;
+                for (int c = 0; c < nc; ++c) {
+                    float D = C.D[c];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float jv = C.jv[k][c], xx = fmaf(alpha, jv, C.jar[k][c]);
+                        if (xx < 0.f) { e1 = fmaf(D * jv, xx, e1); e2 = fmaf(D * jv, jv, e2); }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    float xx = fmaf(alpha, ljv[k], ljar[k]);
+                    if (lsgn[k] != 0.f && xx < 0.f) { e1 = fmaf(lD[k] * ljv[k], xx, e1); e2 = fmaf(lD[k] * ljv[k], ljv[k], e2); }
+                }
+                d1 = qsum(e1, qm) + q1 + 2.f * alpha * q2;
+                d2 = qsum(e2, qm) + 2.f * q2;
+                st.nls++;
+                if (it == 0) { if (d1 >= 0.f) break; }
+                else {
+                    if (fabsf(d1) < gtol) break;
+                    if (d1 < 0.f) lo = alpha; else hi = alpha;
+                }
+                if (it == ls_iter) break;
+                float an = alpha - d1 / d2;
+                if (an <= lo || (hi > 0.f && an >= hi)) an = hi > 0.f ? 0.5f * (lo + hi) : 2.f * (lo > 0.f ? lo : 1e-3f);
+                alpha = an;
+            }
+            if (alpha == 0.f) break;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { ab[r] = fmaf(alpha, sb[r], ab[r]); Mab[r] = fmaf(alpha, Mvb[r], Mab[r]); }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { al[k] = fmaf(alpha, sv[k], al[k]); Mal[k] = fmaf(alpha, Mvl[k], Mal[k]); ljar[k] = fmaf(alpha, ljv[k], ljar[k]); }
+            for (int c = 0; c < nc; ++c)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) C.jar[k][c] = fmaf(alpha, C.jv[k][c], C.jar[k][c]);
+            cost_old = cost;
+            iter++;
+        }
+        st.niter += (leg == 0) ? iter : 0;
+    }
+
+    // ---- sensors of this forward pass (pre-integration state, solver qacc)
+    if (want_sensors) {
+        so.jq[0] = S.q[0]; so.jq[1] = S.q[1]; so.jq[2] = S.q[2];
+        so.acc = V3(ab[0], ab[1], ab[2]) - gB;
+        so.gyro = S.om;
+        so.pos = S.pb;
+        so.linvel = S.vw;
+        so.xaxis = col0(Rb);
+        so.zaxis = col2(Rb);
+        so.vel = vB;
+    }
+    if (DEBUG) {
+        v3 aw = mul(Rb, V3(ab[0], ab[1], ab[2])), a0w = mul(Rb, V3(a0b[0], a0b[1], a0b[2]));
+        if (leg == 0) {
+            if (dbg.qacc) {
+                float* o = dbg.qacc + env * 18;
+                o[0] = aw.x; o[1] = aw.y; o[2] = aw.z; o[3] = ab[3]; o[4] = ab[4]; o[5] = ab[5];
+            }
+            if (dbg.qacc_smooth) {
+                float* o = dbg.qacc_smooth + env * 18;
+                o[0] = a0w.x; o[1] = a0w.y; o[2] = a0w.z; o[3] = a0b[3]; o[4] = a0b[4]; o[5] = a0b[5];
+            }
+            if (dbg.qfrc_bias) {
+                float* o = dbg.qfrc_bias + env * 18;
+                o[0] = fsum.x; o[1] = fsum.y; o[2] = fsum.z; o[3] = nsum.x; o[4] = nsum.y; o[5] = nsum.z;
+            }
+            if (dbg.M) {
+                float* o = dbg.M + (size_t)env * 324;
+                for (int i = 0; i < 6; ++i)
+                    for (int j = 0; j <= i; ++j) { o[i * 18 + j] = Mbb[IX6(i, j)]; o[j * 18 + i] = Mbb[IX6(i, j)]; }
+            }
+        }
+        for (int k = 0; k < 3; ++k) {
+            int d = 6 + 3 * leg + k;
+            if (dbg.qacc) dbg.qacc[env * 18 + d] = al[k];
+            if (dbg.qacc_smooth) dbg.qacc_smooth[env * 18 + d] = a0l[k];
+            if (dbg.qfrc_bias) dbg.qfrc_bias[env * 18 + d] = bias_l[k];
+            if (dbg.M) {
+                float* o = dbg.M + (size_t)env * 324;
+                for (int r = 0; r < 6; ++r) { o[r * 18 + d] = Mbl[r * 3 + k]; o[d * 18 + r] = Mbl[r * 3 + k]; }
+                for (int j = 0; j < 3; ++j) {
+                    int a = k < j ? k : j, b = k < j ? j : k;
+                    int idx = (a == 0) ? b : (a == 1 ? 2 + b : 5);
+                    o[d * 18 + 6 + 3 * leg + j] = Mll[idx];
+                }
+                for (int l2 = 0; l2 < 4; ++l2)
+                    if (l2 != leg)
+                        for (int j = 0; j < 3; ++j) o[d * 18 + 6 + 3 * l2 + j] = 0.f;
+            }
+        }
+    }
+
+    // ---- integrate: (M + h*diag) qacc+ = qfrc_smooth + qfrc_constraint ; semi-implicit update
+    {
+        float Hll[6], Hb[21], rb[6], rl[3], xb[6], xl[3];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Hll[i] = Mll[i];
+        Hll[0] += h * dimp[0]; Hll[3] += h * dimp[1]; Hll[5] += h * dimp[2];
+#pragma unroll
+        for (int i = 0; i < 21; ++i) Hb[i] = Mbb[i];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { Hb[IX6(r, r)] += h * P.base_damp[r]; rb[r] = fsb[r] + fcb[r]; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) rl[k] = fsl[k] + fcl[k];
+        arrow_solve(Hll, Mbl, nullptr, Hb, rb, rl, qm, xb, xl);
+        // warm start for the next step = this step's solver acceleration (world form)
+        S.wl = mul(Rb, V3(ab[0], ab[1], ab[2]));
+        S.wa = V3(ab[3], ab[4], ab[5]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            S.wj[k] = al[k];
+            S.act[k] = fmaf(act_dot[k], P.joint[leg][k].act_fac, S.act[k]);
+            S.qd[k] = fmaf(h, xl[k], S.qd[k]);
+            S.q[k] = fmaf(h, S.qd[k], S.q[k]);
+        }
+        v3 vBn = fma3(h, V3(xb[0], xb[1], xb[2]), vB);
+        S.vw = mul(Rb, vBn);
+        S.om = fma3(h, V3(xb[3], xb[4], xb[5]), S.om);
+        S.pb = fma3(h, S.vw, S.pb);
+        float wn = sqrtf(dot(S.om, S.om));
+        float rw = 1.f, rx = 0.f, ry = 0.f, rz = 0.f;
+        if (wn > 1e-15f) {
+            float sn, cs;
+            sincosf(0.5f * h * wn, &sn, &cs);
+            float s = sn / wn;
+            rw = cs; rx = S.om.x * s; ry = S.om.y * s; rz = S.om.z * s;
+        }
+        S.qw = w * rw - x * rx - y * ry - z * rz;
+        S.qx = w * rx + x * rw + y * rz - z * ry;
+        S.qy = w * ry - x * rz + y * rw + z * rx;
+        S.qz = w * rz + x * ry - y * rx + z * rw;
+        S.time += P.timestep_d;
+    }
+}
