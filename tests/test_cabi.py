@@ -1,0 +1,89 @@
+"""The C-ABI shared library loads, exports every symbol include/quadgym.h declares, parses model blobs
+and reports errors through return codes (no compute calls here: no GPU in this tier)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from quadruped_gym_b200 import _lib
+from quadruped_gym_b200.model import blob as qblob
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "quadgym.h")).read()
+    declared = set(re.findall(r"\b(qg_[a-z0-9_]+)\s*\(", header))
+    declared -= {"qg_counters"}
+    assert declared == set(_lib.SYMBOLS)
+    L = C.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert b"sm_100a" in _lib.lib().qg_version()
+
+
+def test_model_load_and_info(blob):
+    L = _lib.lib()
+    h = C.c_void_p()
+    assert L.qg_model_load(blob, len(blob), C.byref(h)) == 0
+    sizes, ts = (C.c_int * 8)(), C.c_double()
+    assert L.qg_model_info(h, sizes, C.byref(ts)) == 0
+    assert list(sizes) == [19, 18, 12, 14, 13, 25, 5, 33] and ts.value == 0.002
+    L.qg_model_destroy(h)
+
+
+def test_bad_blobs_are_rejected_with_codes(blob):
+    L = _lib.lib()
+    h = C.c_void_p()
+    assert L.qg_model_load(b"not a blob at all", 17, C.byref(h)) == -2          # QG_EBLOB
+    assert b"magic" in L.qg_last_error()
+    assert L.qg_model_load(blob[: len(blob) // 2], len(blob) // 2, C.byref(h)) == -2
+    A = qblob.unpack(blob)
+    A2 = dict(A)
+    del A2["geom_mu"]
+    raw = qblob.pack(A2)
+    assert L.qg_model_load(raw, len(raw), C.byref(h)) == -2 and b"geom_mu" in L.qg_last_error()
+    # outside the supported model class -> QG_EMODEL
+    A3 = {k: v.copy() for k, v in A.items()}
+    A3["jnt_axis"] = A3["jnt_axis"].copy()
+    A3["jnt_axis"][3:6] = [1.0, 0.0, 0.0]          # first hinge about x
+    raw = qblob.pack(A3)
+    assert L.qg_model_load(raw, len(raw), C.byref(h)) == -3 and b"axis" in L.qg_last_error()
+    A4 = {k: v.copy() for k, v in A.items()}
+    A4["opt_i"][1] = 1                              # elliptic cone: not implemented yet
+    raw = qblob.pack(A4)
+    assert L.qg_model_load(raw, len(raw), C.byref(h)) == -3 and b"elliptic" in L.qg_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(-3, "qg_model_load")
+
+
+def test_no_cpu_fallback(blob):
+    """Without a CUDA device the batch constructor fails loudly (QG_ECUDA); with one it succeeds."""
+    import torch
+    L = _lib.lib()
+    h, b = C.c_void_p(), C.c_void_p()
+    assert L.qg_model_load(blob, len(blob), C.byref(h)) == 0
+    rc = L.qg_batch_create(h, 8, 0, C.byref(b))
+    if torch.cuda.is_available():
+        assert rc == 0
+        L.qg_batch_destroy(b)
+    else:
+        assert rc == -4 and b"no CPU fallback" in L.qg_last_error()
+        from quadruped_gym_b200 import VecQuadrupedEnv
+        with pytest.raises(_lib.QuadGymLibraryError):
+            VecQuadrupedEnv(4, "cpu")
+    assert L.qg_batch_create(h, 0, 0, C.byref(b)) == -1     # QG_EINVAL
+    L.qg_model_destroy(h)
+
+
+def test_product_does_not_import_the_oracle():
+    """The product path may not route through oracle/ (test infrastructure)."""
+    pkg = os.path.join(ROOT, "quadruped_gym_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, re.M), f
+                assert "libqgoracle" not in txt and "qg_oracle.h" not in txt and "qgo_step" not in txt, f

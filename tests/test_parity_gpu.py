@@ -1,0 +1,352 @@
+"""GPU parity tests: the sm_100a path (through the C ABI) against the float64 CPU oracle on the same
+seeded inputs.  Tolerances (fp32 device arithmetic vs fp64 oracle), stated per quantity:
+
+  * mass matrix, bias forces:      1e-5 relative to the largest entry
+  * qacc_smooth / qacc:            1e-4 relative to max|qacc| per env  (north star: 1e-4 contact-free,
+                                   1e-3 with contacts) -- contact rows require the same contact set
+  * next qpos / qvel / act:        1e-5 absolute on qpos/act, 1e-4 relative on qvel
+  * sensordata:                    1e-5 absolute, accelerometer channels 1e-4 * max(1, |qacc|max)
+  * reward terms / termination:    exact given equal state (float64 formulas on float32 inputs)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.oracle import OracleData
+from tests import ref_formulas as F
+from tests.conftest import rollout_states
+
+pytestmark = pytest.mark.gpu
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "env_traces.npz"))
+
+
+@pytest.fixture(scope="module")
+def Vec():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from quadruped_gym_b200 import VecQuadrupedEnv
+    return VecQuadrupedEnv
+
+
+def _oracle_at(om, st32, time, ctrl, e):
+    d = OracleData(om)
+    d.set_state(st32["qpos"][e].astype(np.float64), st32["qvel"][e].astype(np.float64), st32["act"][e].astype(np.float64),
+                st32["warm"][e].astype(np.float64), time[e], ctrl[e].astype(np.float64))
+    return d
+
+
+def _bform(M, R):
+    T = np.eye(18)
+    T[:3, :3] = R
+    return T.T @ M @ T
+
+
+@pytest.fixture(scope="module")
+def teacher_forced(Vec, oracle_model):
+    """384 states from oracle rollouts (flight, landing, standing, stumbling), one debug step on the GPU."""
+    n = 384
+    st = rollout_states(oracle_model, n, 150, seed=11)
+    st32 = {k: v.astype(np.float32) for k, v in st.items() if k != "time"}
+    env = Vec(n, "cuda:0", auto_reset=False)
+    env.set_state(qpos=st32["qpos"], qvel=st32["qvel"], act=st32["act"], qacc_warmstart=st32["warm"], time=st["time"], ctrl=st32["ctrl"])
+    ctrl = np.random.default_rng(3).uniform(-1.2, 1.2, (n, 12)).astype(np.float32)
+    out = {k: v.cpu().numpy() for k, v in env.debug_step(ctrl).items()}
+    nxt = {"qpos": env.data.qpos.cpu().numpy(), "qvel": env.data.qvel.cpu().numpy(), "act": env.data.act.cpu().numpy(),
+           "warm": env.data.qacc_warmstart.cpu().numpy(), "time": env.data.time.cpu().numpy()}
+    ora = [_oracle_at(oracle_model, st32, st["time"], ctrl, e) for e in range(n)]
+    for d in ora:
+        d.forward()
+    env.close()
+    return n, st, st32, ctrl, out, nxt, ora
+
+
+def test_smooth_dynamics_stage_parity(teacher_forced):
+    n, st, st32, ctrl, out, nxt, ora = teacher_forced
+    for e, d in enumerate(ora):
+        R = d.xmat[9:18].reshape(3, 3)
+        MB = _bform(d.M.copy(), R)
+        assert np.abs(out["M"][e] - MB).max() <= 1e-5 * np.abs(MB).max()
+        bias = d.qfrc_bias.copy()
+        bias[:3] = R.T @ bias[:3]
+        assert np.abs(out["qfrc_bias"][e] - bias).max() <= 1e-5 * max(1.0, np.abs(bias).max())
+        assert np.abs(out["qacc_smooth"][e] - d.qacc_smooth).max() <= 1e-4 * max(1.0, np.abs(d.qacc_smooth).max())
+
+
+def test_contact_sets_and_constrained_acceleration(teacher_forced):
+    n, st, st32, ctrl, out, nxt, ora = teacher_forced
+    ncon = np.array([d.ncon for d in ora])
+    nefc = np.array([d.nefc for d in ora])
+    same = (out["counts"][:, 0] == ncon) & (out["counts"][:, 1] == nefc)
+    assert same.mean() >= 0.98            # contact-set flips only at fp32-vs-fp64 ties
+    assert (ncon > 0).sum() >= 100 and (ncon == 0).sum() >= 20    # the sample covers both regimes
+    for e, d in enumerate(ora):
+        if not same[e]:
+            continue
+        tol = 1e-4 if d.nefc == 0 else 1e-3
+        assert np.abs(out["qacc"][e] - d.qacc).max() <= tol * max(1.0, np.abs(d.qacc).max()), (e, d.ncon)
+    # solver effort comparable to the oracle's
+    assert out["counts"][:, 2].mean() <= np.mean([d.solver_niter for d in ora]) + 1.0
+
+
+def test_sensordata_parity_and_lag(teacher_forced):
+    n, st, st32, ctrl, out, nxt, ora = teacher_forced
+    same = np.array([out["counts"][e, 0] == d.ncon for e, d in enumerate(ora)])
+    for e, d in enumerate(ora):
+        if not same[e]:
+            continue
+        s, g = d.sensordata.copy(), out["sensordata"][e]
+        acc_tol = 1e-3 * max(1.0, np.abs(d.qacc).max())
+        assert np.abs(g[12:15] - s[12:15]).max() <= acc_tol
+        s[12:15] = g[12:15] = 0
+        assert np.abs(g - s).max() <= 1e-5
+        # sensordata is the PRE-integration state (quadruped.py:167 returns the last forward pass)
+        assert np.array_equal(g[:12], st32["qpos"][e, 7:])
+        assert np.array_equal(g[15:18], st32["qvel"][e, 3:6])
+
+
+def test_next_state_parity(teacher_forced, oracle_model):
+    n, st, st32, ctrl, out, nxt, ora = teacher_forced
+    same = np.array([out["counts"][e, 0] == d.ncon for e, d in enumerate(ora)])
+    for e in range(n):
+        if not same[e]:
+            continue
+        d = _oracle_at(oracle_model, st32, st["time"], ctrl, e)
+        d.step()
+        assert np.abs(nxt["qpos"][e] - d.qpos).max() <= 1e-5
+        assert np.abs(nxt["act"][e] - d.act).max() <= 1e-5
+        assert np.abs(nxt["qvel"][e] - d.qvel).max() <= 1e-4 * max(1.0, np.abs(d.qvel).max())
+        assert np.abs(nxt["warm"][e] - d.qacc_warmstart).max() <= 1e-3 * max(1.0, np.abs(d.qacc_warmstart).max())
+        assert nxt["time"][e] == d.time            # fp64 time accumulation, bit exact
+
+
+def test_joint_limit_states(Vec, oracle_model):
+    """Edge case: joints pushed beyond their ranges with servos driving further out (limit rows active)."""
+    n = 32
+    rng = np.random.default_rng(5)
+    qpos = np.tile(np.r_[0, 0, 1.0, 1, 0, 0, 0, np.tile(np.deg2rad([-45, 37.5, 0]), 4)], (n, 1)).astype(np.float32)
+    lo, hi = np.tile(np.deg2rad([-45, -45, -90]), 4), np.tile(np.deg2rad([45, 120, 90]), 4)
+    below = rng.random((n, 12)) < 0.5
+    qpos[:, 7:] = np.where(below, lo - rng.uniform(0.01, 0.2, (n, 12)), hi + rng.uniform(0.01, 0.2, (n, 12)))
+    act = np.where(below, -1.5, 1.5).astype(np.float32)
+    qvel = (rng.normal(size=(n, 18)) * 0.5).astype(np.float32)
+    env = Vec(n, "cuda:0", auto_reset=False)
+    env.set_state(qpos=qpos, qvel=qvel, act=act, qacc_warmstart=np.zeros((n, 18), np.float32), time=np.zeros(n), ctrl=np.zeros((n, 12), np.float32))
+    ctrl = np.where(below, -1.0, 1.0).astype(np.float32)
+    out = {k: v.cpu().numpy() for k, v in env.debug_step(ctrl).items()}
+    active = 0
+    for e in range(n):
+        d = OracleData(oracle_model)
+        d.set_state(qpos[e].astype(np.float64), qvel[e].astype(np.float64), act[e].astype(np.float64), np.zeros(18), 0.0, ctrl[e].astype(np.float64))
+        d.forward()
+        assert out["counts"][e, 1] == d.nefc == 12
+        active += int((d.efc_force > 0).sum())
+        assert np.abs(out["qacc"][e] - d.qacc).max() <= 1e-3 * max(1.0, np.abs(d.qacc).max())
+    assert active > n * 6
+    env.close()
+
+
+def test_open_loop_rollout_bounded_divergence(Vec, oracle_model):
+    """64 envs from reset through the 10 cm drop, landing and 40 more env steps under random actions:
+    median error stays at fp32 round-off level; the worst env is bounded (contact-set flips amplify)."""
+    n, T = 64, 60
+    env = Vec(n, "cuda:0", auto_reset=False, frame_skip=4)
+    obs0, _ = env.reset()
+    assert torch.count_nonzero(obs0) == 0            # reset observation is all zeros (quadruped.py:120,138)
+    rng = np.random.default_rng(21)
+    acts = np.repeat(rng.uniform(-1, 1, (T // 5, n, 12)).astype(np.float32), 5, axis=0)
+    ds = [OracleData(oracle_model) for _ in range(n)]
+    for d in ds:
+        d.ctrl[:] = [0, 0, -0.5] * 4
+    med, worst = [], []
+    for t in range(T):
+        obs, rew, term, trunc, info = env.step(torch.from_numpy(acts[t]).cuda())
+        o = obs.cpu().numpy().astype(np.float64)
+        ref = np.zeros((n, 33))
+        for e, d in enumerate(ds):
+            d.env_step(acts[t, e].astype(np.float64), 4)
+            ref[e] = d.sensordata
+        err = np.abs(o - ref)
+        err[:, 12:15] = 0
+        med.append(np.median(err.max(1)))
+        worst.append(err.max())
+        assert not bool(trunc.any())
+    assert max(med[:20]) < 1e-5          # contact-free flight: round-off only
+    assert max(med) < 1e-4               # through landing and stance
+    assert np.median(worst) < 1e-3
+    qg, qo = env.data.qpos.cpu().numpy(), np.array([d.qpos.copy() for d in ds])
+    assert np.median(np.abs(qg - qo).max(1)) < 1e-4
+    env.close()
+
+
+def test_golden_trace_A_env_step_semantics(Vec):
+    """The reference's own QuadrupedEnv (run on the oracle physics) vs VecQuadrupedEnv on the same actions:
+    clip, frame_skip loop, lagged sensordata, README reward trio, time, termination."""
+    from quadruped_gym_b200.envs import rewards as R
+    env = Vec(2, "cuda:0", auto_reset=False, reward_fns={"forward": R.forward_velocity(1.0), "control_cost": R.ctrl_sq(-0.1),
+                                                          "alive_bonus": R.alive_bonus(1.0)})
+    obs, _ = env.reset()
+    assert np.array_equal(obs.cpu().numpy()[0], G["A_obs0"])
+    T = 120   # through drop + landing; later steps diverge chaotically at fp32 level
+    for t in range(T):
+        a = torch.from_numpy(np.stack([G["A_actions"][t]] * 2)).cuda()     # unclipped actions: the env clips
+        obs, rew, term, trunc, info = env.step(a)
+        o = obs[0].cpu().numpy()
+        err = np.abs(o - G["A_obs"][t])
+        err[12:15] /= 100.0
+        assert err.max() < (1e-4 if t < 25 else 5e-3), (t, err.max())
+        # reward exact given the device's own state: float64 formulas on float32 inputs
+        qv = env.data.qvel[0].cpu().numpy().astype(np.float64)
+        ctrl = env.data.ctrl[0].cpu().numpy().astype(np.float64)
+        assert np.array_equal(ctrl, np.clip(G["A_actions"][t], -1, 1).astype(np.float64))
+        total, comps = F.readme_reward(qv, ctrl)
+        assert rew[0].item() == np.float32(total)
+        for k, c in zip(("forward", "control_cost", "alive_bonus"), comps):
+            assert info["reward_components"][k][0].item() == np.float32(c)
+        assert abs(rew[0].item() - G["A_reward"][t]) < 5e-3
+        assert float(env.data.time[0]) == G["A_time"][t]
+        assert bool(term[0]) == bool(G["A_terminated"][t]) and not bool(trunc[0])
+        assert torch.equal(obs[0], obs[1]) and rew[0] == rew[1]           # determinism across lanes
+    env.close()
+
+
+@pytest.mark.parametrize("frame_skip,max_time,want", [(4, 10.0, 1250), (10, 20.0, 1001)])
+def test_time_limit_termination_index(Vec, frame_skip, max_time, want):
+    """fp64 time accumulation on the device: terminated first at env.step() #1250 / #1001 (golden trace B)."""
+    assert int(G["B4_first_terminated_step" if frame_skip == 4 else "B10_first_terminated_step"]) == want
+    env = Vec(4, "cuda:0", auto_reset=False, frame_skip=frame_skip, max_time=max_time)
+    env.reset()
+    a = torch.zeros((4, 12), device="cuda")
+    first = None
+    for i in range(1, want + 2):
+        _, _, term, trunc, _ = env.step(a)
+        if first is None and bool(term.any()):
+            first = i
+            assert bool(term.all())
+    assert first == want
+    env.close()
+
+
+def test_fused_reward_terms_exact(Vec):
+    """Every fused term equals the reference formula (tests/ref_formulas.py, pinned by golden trace C)
+    evaluated in float64 on the device's own float32 sensordata / ctrl."""
+    from quadruped_gym_b200.envs import rewards as R
+    n = 8
+    fns = {"alive": R.alive_bonus(10.0), "cc": R.control_cost(-2.0, 0.8), "ori": R.exp_orientation(10.0),
+           "h": R.exp_body_height(-50.0, 0.13), "post": R.joint_posture_cost(-1.0), "fwd": R.forward_reward(5.0),
+           "drift": R.no_drift_reward(-3.0), "o": R.orientation_reward(1.0), "hc": R.body_height_cost(1.0, 0.12)}
+    env = Vec(n, "cuda:0", auto_reset=False, reward_fns=fns)
+    env.reset()
+    rng = np.random.default_rng(8)
+    ccs = [F.ControlCost() for _ in range(n)]
+    for t in range(40):
+        a = rng.uniform(-1, 1, (n, 12)).astype(np.float32)
+        obs, rew, term, trunc, info = env.step(torch.from_numpy(a).cuda())
+        o = obs.cpu().numpy().astype(np.float64)
+        for e in range(n):
+            ctrl = a[e].astype(np.float64)
+            want = {"alive": 10.0 * 1, "cc": -2.0 * ccs[e](ctrl), "ori": 10.0 * F.exp_dist(F.orientation_reward(o[e])),
+                    "h": -50.0 * F.exp_dist(F.body_height_cost(o[e], 0.13)), "post": -1.0 * F.joint_posture_cost(ctrl),
+                    "fwd": 5.0 * F.forward_reward(o[e]), "drift": -3.0 * F.no_drift_reward(o[e]),
+                    "o": F.orientation_reward(o[e]), "hc": F.body_height_cost(o[e], 0.12)}
+            for k, v in want.items():
+                got = info["reward_components"][k][e].item()
+                if k in ("ori", "h", "post"):          # exp / sqrt: 1 ulp of float64 differences survive the f32 cast rarely
+                    assert got == pytest.approx(np.float32(v), rel=2e-7), k
+                else:
+                    assert got == np.float32(v), k
+            total = 0.0
+            for k in fns:
+                total += want[k]
+            assert rew[e].item() == pytest.approx(np.float32(total), rel=1e-6)
+    env.close()
+
+
+@pytest.mark.parametrize("tag", ["D80", "D95"])
+def test_flip_termination_and_auto_reset(Vec, tag):
+    """Golden trace D: rolled start; terminated == (lagged zaxis_z < 0) exactly; auto-reset returns the zero
+    observation, keeps the terminal one, and restarts time."""
+    from quadruped_gym_b200.envs import rewards as R
+    env = Vec(3, "cuda:0", auto_reset=True, termination_fns={"flip": R.flip_termination()})
+    env.reset()
+    half = 0.5 * np.deg2rad(float(G[tag + "_roll_deg"]))
+    q = env.data.qpos.cpu().numpy()
+    q[:, 3:7] = [np.cos(half), np.sin(half), 0, 0]
+    env.set_state(qpos=q)
+    a = torch.zeros((3, 12), device="cuda")
+    flips = 0
+    for t in range(len(G[tag + "_terminated"])):
+        obs, rew, term, trunc, info = env.step(a)
+        tobs = info["terminal_observation"]
+        z = torch.where(term, tobs[:, 29], obs[:, 29])
+        assert torch.equal(term, z < 0)                        # exact given the device's own sensordata
+        if bool(term[0]):
+            flips += 1
+            assert torch.count_nonzero(obs[0]) == 0            # reset observation
+            assert float(env.data.time[0]) == 0.0
+            assert np.allclose(env.data.qpos[0].cpu().numpy()[:7], [0, 0, 0.13, 1, 0, 0, 0])
+            break
+        elif abs(G[tag + "_zaxis_z"][t]) > 0.02:
+            assert bool(G[tag + "_terminated"][t]) is False
+            assert abs(obs[0, 29].item() - G[tag + "_zaxis_z"][t]) < 0.02
+    assert flips == 1
+    t_flip = int(np.argmax(G[tag + "_terminated"]))
+    assert abs(t - t_flip) <= 2
+    env.close()
+
+
+def test_shard_invariance_and_host_path(Vec):
+    """Two half-batches with env_offset == one full batch (no exchange between environments), and the
+    HOST-buffer C-ABI call returns the same numbers as the device call."""
+    n = 64
+    rng = np.random.default_rng(13)
+    acts = rng.uniform(-1, 1, (30, n, 12)).astype(np.float32)
+    full = Vec(n, "cuda:0", auto_reset=True)
+    halves = [Vec(n // 2, "cuda:0", auto_reset=True, env_offset=i * n // 2) for i in range(2)]
+    host = Vec(n, "cuda:0", auto_reset=True)
+    for e in (full, host, *halves):
+        e.reset()
+    for t in range(30):
+        o, r, te, _, _ = full.step(torch.from_numpy(acts[t]).cuda())
+        parts = [h.step(torch.from_numpy(acts[t, i * n // 2:(i + 1) * n // 2]).cuda()) for i, h in enumerate(halves)]
+        assert torch.equal(o, torch.cat([p[0] for p in parts]))
+        assert torch.equal(r, torch.cat([p[1] for p in parts]))
+        ho, hr, hte, _, _ = host.step_host(acts[t])
+        assert np.array_equal(ho, o.cpu().numpy()) and np.array_equal(hr, r.cpu().numpy()) and np.array_equal(hte, te.cpu().numpy())
+    c = full.counters()
+    assert c["physics_steps"] == n * 30 * 4 and c["diverged"] == 0 and c["contact_overflow"] == 0
+    for e in (full, host, *halves):
+        e.close()
+
+
+def test_non_finite_state_guard(Vec):
+    """mj_checkPos analogue: a non-finite state resets that environment only and is counted."""
+    env = Vec(4, "cuda:0", auto_reset=False)
+    env.reset()
+    q = env.data.qpos.cpu().numpy()
+    q[2, 8] = np.nan
+    env.set_state(qpos=q)
+    obs, *_ = env.step(torch.zeros((4, 12), device="cuda"))
+    assert bool(torch.isfinite(obs).all())
+    assert env.counters()["diverged"] == 1
+    assert torch.equal(obs[0], obs[1]) and torch.equal(obs[0], obs[3])
+    env.close()
+
+
+def test_single_env_shim_matches_reference_signature(Vec):
+    from quadruped_gym_b200 import QuadrupedEnv
+    env = QuadrupedEnv()
+    env.reward_fns = {"forward": lambda: env.data.qvel[0], "alive": lambda: 1.0}     # README.md:65-78 style callables
+    obs, info = env.reset()
+    assert obs.shape == (33,) and obs.dtype == np.float64 and info == {} and not obs.any()
+    o, r, te, tr, info = env.step(np.full(12, 3.0, dtype=np.float32))
+    assert o.shape == (33,) and isinstance(r, float) and te is False and tr is False
+    assert set(info) == {"time", "reward_components"} and info["time"] == pytest.approx(0.008)
+    assert np.array_equal(env.data.ctrl, np.ones(12))           # clipped to the action space (quadruped.py:160)
+    assert r == pytest.approx(env.data.qvel[0] + 1.0, abs=1e-6)
+    assert env.action_space.shape == (12,) and env.observation_space.shape == (33,)
+    env.close()
+    with pytest.raises(FileNotFoundError):
+        QuadrupedEnv(model_path="/nonexistent/scene.xml")        # quadruped.py:55-56
