@@ -60,6 +60,13 @@ def _cpu_worker(args):
 _POOL = {}
 
 
+def _close_pools():
+    for p in _POOL.values():
+        p.terminate()
+        p.join()
+    _POOL.clear()
+
+
 def _pool(procs):
     import multiprocessing as mp
     if procs not in _POOL:
@@ -210,16 +217,18 @@ def run_ours(a):
     ctr = env.counters(reset=True)
 
     # ---- end to end through the host-buffer C-ABI call (H2D + kernel + D2H inside the timed region)
-    hpool = [np.ascontiguousarray(p.cpu().numpy()) for p in pool]
-    for i in range(3):
-        env.step_host(hpool[i % 8])
-    barrier()
-    te0 = time.perf_counter()
-    for i in range(a.steps):
-        env.step_host(hpool[i % 8])
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - te0
-    barrier()
+    e2e_s = float("nan")
+    if not a.profile:
+        hpool = [np.ascontiguousarray(p.cpu().numpy()) for p in pool]
+        for i in range(3):
+            env.step_host(hpool[i % 8])
+        barrier()
+        te0 = time.perf_counter()
+        for i in range(a.steps):
+            env.step_host(hpool[i % 8])
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - te0
+        barrier()
 
     t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     cvec = torch.tensor([float(ctr[k]) for k in sorted(ctr)], dtype=torch.float64, device=dev)
@@ -240,15 +249,15 @@ def run_ours(a):
             pass
         hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
         import ctypes
-        tf = ctypes.c_double()
-        _lib.lib().qg_fp32_peak(local, 4096, ctypes.byref(tf))
+        tf = ctypes.c_double(0.0)
+        if not a.profile:
+            _lib.lib().qg_fp32_peak(local, 4096, ctypes.byref(tf))
         launch_ms = float(np.mean(step_ms))
         algo_bytes = 737.0 * envs  # 737 B per env.step() per env
         hbm_ach = algo_bytes / (launch_ms * 1e-3) / 1e9
         fp32_ach = fl * envs * fs / (launch_ms * 1e-3) / 1e12
         cores = os.cpu_count() or 1
-        r1, _ = cpu_rate(1, 3000, fs, max_time)
-        rp, _ = cpu_rate(cores, 3000, fs, max_time)
+        r1, rp = (float("nan"), float("nan")) if a.profile else (cpu_rate(1, 3000, fs, max_time)[0], cpu_rate(cores, 3000, fs, max_time)[0])
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -284,11 +293,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
+    ap.add_argument("--profile", action="store_true", help="ncu runs: skip the e2e, FP32-peak and CPU-baseline legs")
     a = ap.parse_args()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_ours(a)
+    try:
+        if a.impl == "reference":
+            run_reference(a)
+        else:
+            run_ours(a)
+    finally:
+        _close_pools()
 
 
 if __name__ == "__main__":

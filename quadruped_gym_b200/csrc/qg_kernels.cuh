@@ -31,7 +31,7 @@ DI uint4 philox4x32(uint2 key, uint4 c) {
     return c;
 }
 
-DI void load_lane(const float4* __restrict__ S, int N, int env, int leg, LaneState& L, int& episode, float& first_cc,
+DI void load_lane(const float4* __restrict__ S, int N, int env, int leg, LaneState& L, int& episode, double& first_cc,
                   int& flags) {
     float4 p = ldS(S, QG_PL_POS, N, env), q = ldS(S, QG_PL_QUAT, N, env), v = ldS(S, QG_PL_VLIN, N, env);
     float4 o = ldS(S, QG_PL_VANG, N, env), a = ldS(S, QG_PL_WLIN, N, env), b = ldS(S, QG_PL_WANG, N, env);
@@ -44,8 +44,8 @@ DI void load_lane(const float4* __restrict__ S, int N, int env, int leg, LaneSta
     L.wa = V3(b.x, b.y, b.z);
     L.time = __hiloint2double(__float_as_int(t.y), __float_as_int(t.x));
     episode = __float_as_int(t.z);
-    first_cc = t.w;
     flags = __float_as_int(x.x);
+    first_cc = __hiloint2double(__float_as_int(x.z), __float_as_int(x.y));
     int pl = QG_PL_LEG0 + 4 * leg;
     float4 l0 = ldS(S, pl, N, env), l1 = ldS(S, pl + 1, N, env), l2 = ldS(S, pl + 2, N, env), l3 = ldS(S, pl + 3, N, env);
     L.q[0] = l0.x; L.q[1] = l0.y; L.q[2] = l0.z; L.qd[0] = l0.w;
@@ -54,7 +54,7 @@ DI void load_lane(const float4* __restrict__ S, int N, int env, int leg, LaneSta
     L.ctrl[0] = l3.x; L.ctrl[1] = l3.y; L.ctrl[2] = l3.z;
 }
 
-DI void store_lane(float4* __restrict__ S, int N, int env, int leg, const LaneState& L, int episode, float first_cc,
+DI void store_lane(float4* __restrict__ S, int N, int env, int leg, const LaneState& L, int episode, double first_cc,
                    int flags) {
     if (leg == 0) {
         stS(S, QG_PL_POS, N, env, make_float4(L.pb.x, L.pb.y, L.pb.z, 0.f));
@@ -67,8 +67,9 @@ DI void store_lane(float4* __restrict__ S, int N, int env, int leg, const LaneSt
         stS(S, QG_PL_WANG, N, env, make_float4(L.wa.x, L.wa.y, L.wa.z, 0.f));
     } else {
         stS(S, QG_PL_TIME, N, env, make_float4(__int_as_float(__double2loint(L.time)), __int_as_float(__double2hiint(L.time)),
-                                                __int_as_float(episode), first_cc));
-        stS(S, QG_PL_AUX, N, env, make_float4(__int_as_float(flags), 0.f, 0.f, 0.f));
+                                                __int_as_float(episode), 0.f));
+        stS(S, QG_PL_AUX, N, env, make_float4(__int_as_float(flags), __int_as_float(__double2loint(first_cc)),
+                                               __int_as_float(__double2hiint(first_cc)), 0.f));
     }
     int pl = QG_PL_LEG0 + 4 * leg;
     stS(S, pl, N, env, make_float4(L.q[0], L.q[1], L.q[2], L.qd[0]));
@@ -143,7 +144,7 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
     if (env < N) {
         LaneState L;
         int episode, flags;
-        float first_cc;
+        double first_cc;
         load_lane(S, N, env, leg, L, episode, first_cc, flags);
         float prev_ctrl[3] = {L.ctrl[0], L.ctrl[1], L.ctrl[2]};
 #pragma unroll
@@ -195,8 +196,8 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
                         double sq[12];
                         for (int k = 0; k < 12; ++k) { double d = call[k] - pall[k]; sq[k] = d * d; }
                         double cost = np_sum12(sq);
-                        if (!(flags & 1)) { first_cc = (float)cost; flags |= 1; }
-                        v = p * (double)first_cc + (1.0 - p) * cost;
+                        if (!(flags & 1)) { first_cc = cost; flags |= 1; }
+                        v = p * first_cc + (1.0 - p) * cost;
                     } break;
                     case 6: v = (double)so.zaxis.z; break;
                     case 7: v = fabs((double)so.pos.z - p); break;
@@ -288,9 +289,9 @@ __global__ void qg_reset_kernel(const QgModelC* __restrict__ gm, float4* __restr
     if (mask && !mask[env]) return;
     LaneState L;
     int episode, flags;
-    float first_cc;
+    double first_cc;
     load_lane(S, N, env, leg, L, episode, first_cc, flags);
-    if (clear_env_state) { episode = 0; flags = 0; first_cc = 0.f; }
+    if (clear_env_state) { episode = 0; flags = 0; first_cc = 0.0; }
     else episode++;
     reset_lane(*gm, L, leg, opts, env, episode);
     store_lane(S, N, env, leg, L, episode, first_cc, flags);
@@ -304,7 +305,7 @@ __global__ void qg_get_state_kernel(const float4* __restrict__ S, int N, float* 
     if (env >= N) return;
     LaneState L;
     int episode, flags;
-    float first_cc;
+    double first_cc;
     load_lane(S, N, env, leg, L, episode, first_cc, flags);
     for (int k = 0; k < 3; ++k) {
         if (qpos) qpos[(size_t)env * 19 + 7 + 3 * leg + k] = L.q[k];
@@ -337,7 +338,7 @@ __global__ void qg_set_state_kernel(float4* __restrict__ S, int N, const float* 
     if (env >= N) return;
     LaneState L;
     int episode, flags;
-    float first_cc;
+    double first_cc;
     load_lane(S, N, env, leg, L, episode, first_cc, flags);
     for (int k = 0; k < 3; ++k) {
         if (qpos) L.q[k] = qpos[(size_t)env * 19 + 7 + 3 * leg + k];

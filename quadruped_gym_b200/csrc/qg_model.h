@@ -23,8 +23,8 @@
 #define QG_PL_VANG 3    // base angular velocity (body)      x y z _
 #define QG_PL_WLIN 4    // qacc_warmstart[0:3] (world)
 #define QG_PL_WANG 5    // qacc_warmstart[3:6]
-#define QG_PL_TIME 6    // time (double in .x/.y), episode counter (int in .z), first control cost (.w)
-#define QG_PL_AUX 7     // flags (.x as int: bit0 = first control cost set), spare
+#define QG_PL_TIME 6    // time (double in .x/.y), episode counter (int in .z)
+#define QG_PL_AUX 7     // flags (.x as int: bit0 = first control cost set), first control cost (double in .y/.z)
 #define QG_PL_LEG0 8    // 4 planes per leg:
                         //   +0: q0 q1 q2 qd0   +1: qd1 qd2 act0 act1   +2: act2 w0 w1 w2
                         //   +3: ctrl0 ctrl1 ctrl2 _      (data.ctrl; also previous_ctrl of control_cost)
