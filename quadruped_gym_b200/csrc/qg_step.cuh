@@ -16,6 +16,11 @@
 //     eliminates its own 3x3 block in registers; the 6x6 Schur complement is summed across the
 //     quad with two xor-shuffles per value and factorised redundantly by all four lanes.
 // No shared-memory scratch, no __syncthreads and no cross-quad communication on the step path.
+//
+// Code-size discipline (the first version was 270 KB of SASS and stalled on instruction fetch): the
+// collision code exists once (rolled loop over the lane's geoms), and the three SPD solves of a step
+// (unconstrained acceleration, Newton direction, implicit integration) share ONE inlined arrow_solve
+// inside a small phase machine.
 #pragma once
 #include "qg_math.cuh"
 #include "qg_model.h"
@@ -47,7 +52,7 @@ struct Contacts {
     int n;
 };
 
-DI float impedance(float r, float d0, float dmax, float width, float mid, float power) {
+__device__ __noinline__ float impedance(float r, float d0, float dmax, float width, float mid, float power) {
     float x = fabsf(r) / fmaxf(1e-15f, width), y;
     if (x >= 1.f) y = 1.f;
     else if (x <= 0.f) y = 0.f;
@@ -59,76 +64,9 @@ DI float impedance(float r, float d0, float dmax, float width, float mid, float 
 }
 
 // ---------------------------------------------------------------------------------------------
-// plane-vs-hull collision of the geoms this lane owns at one tree level (mjc_PlaneConvex restated)
-DI void collide_level(const QgModelC& P, const float4* __restrict__ verts, const int* __restrict__ vert_edge,
-                      const int* __restrict__ mesh_edge, int leg, int g0, int g1, int level,
-                      v3 pk, const m3& Rk, v3 up, float zb, Contacts& C, StepStats& st) {
-    for (int g = g0; g < g1; ++g) {
-        const QgGeomC& G = P.geom[leg][g];
-        v3 ctr = pk + mul(Rk, ld3(G.pos));
-        float zc = zb + dot(up, ctr);
-        m3 RB = matmul(Rk, ldm3(G.R));  // mesh frame -> B
-        v3 dl = tmul(RB, up);           // "up" in the mesh frame
-        float ext = fmaf(fabsf(dl.x), G.half[0], fmaf(fabsf(dl.y), G.half[1], fabsf(dl.z) * G.half[2]));
-        float margin = G.margin;
-        if (zc - ext > margin) continue;  // oriented-box cull (conservative; same contacts as any cull)
-        const float4* __restrict__ vt = verts + G.vert0;
-        int nvert = G.nvert, best = 0;
-        float hbest = 3.0e38f;
-        for (int i = 0; i < nvert; ++i) {
-            float4 v = vt[i];
-            float h = fmaf(dl.x, v.x, fmaf(dl.y, v.y, dl.z * v.z));
-            if (h < hbest) { hbest = h; best = i; }
-        }
-        st.nvert += nvert;
-        if (zc + hbest > margin) continue;
-        // support vertex first, then its hull-graph neighbours (up to 4 contacts per geom)
-        const int* __restrict__ e = mesh_edge + G.edge0 + __ldg(vert_edge + G.vert0 + best);
-        int cnt = 0, cand = best;
-        v3 prev0 = V3(0, 0, 0), prev1 = prev0, prev2 = prev0;
-        for (;;) {
-            float4 v = vt[cand];
-            v3 xv = ctr + mul(RB, V3(v.x, v.y, v.z));
-            float dv = zb + dot(up, xv);
-            bool ok = (cnt == 0) || (dv <= margin);
-            if (ok && cnt > 0) {
-                v3 e0 = xv - prev0, e1 = xv - prev1, e2 = xv - prev2;
-                if (dot(e0, e0) < G.tol2) ok = false;
-                if (!P.rule_first) {
-                    if (cnt > 1 && dot(e1, e1) < G.tol2) ok = false;
-                    if (cnt > 2 && dot(e2, e2) < G.tol2) ok = false;
-                }
-            }
-            if (ok) {
-                if (cnt == 0) prev0 = xv; else if (cnt == 1) prev1 = xv; else if (cnt == 2) prev2 = xv;
-                cnt++;
-                if (dv < margin) {  // includemargin: rows are instantiated only for dist < margin
-                    if (C.n < QG_MAXCON_LANE) {
-                        int c = C.n++;
-                        v3 xc = fma3(-0.5f * dv, up, xv);
-                        float r = dv - margin;
-                        float imp = impedance(r, G.d0, G.dmax, G.width, G.mid, G.power);
-                        C.x[c] = xc.x; C.y[c] = xc.y; C.z[c] = xc.z;
-                        C.D[c] = 1.f / fmaxf(1e-15f, (1.f - imp) / imp * G.Rfac);
-                        C.mu[c] = G.mu;
-                        C.Bd[c] = G.B;
-                        C.Kr[c] = G.K * imp * r;
-                        C.lev[c] = level;
-                    } else st.overflow++;
-                }
-            }
-            if (cnt >= 4) break;
-            int nb = __ldg(e++);
-            if (nb < 0) break;
-            cand = nb;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // arrow-structured SPD solve  [Abb Abl; Alb All] [xb; xl] = [rb; rl]
 //   All (3x3 sym: 00 01 02 11 12 22) and Abl (6x3, [r*3+c]) are lane-local,
-//   Abb = Acommon (identical on the 4 lanes) + sum over lanes of Alocal (may be NULL),
+//   Abb = Acommon (identical on the 4 lanes) + sum over lanes of Alocal,
 //   rb is identical on all lanes.
 DI void arrow_solve(const float* All, const float* Abl, const float* Alocal, const float* Acommon,
                     const float* rb, const float* rl, unsigned qm, float* xb, float* xl) {
@@ -157,7 +95,7 @@ DI void arrow_solve(const float* All, const float* Abl, const float* Alocal, con
 #pragma unroll
         for (int j = 0; j <= i; ++j) {
             float s = fmaf(Abl[i * 3], Y[j * 3], fmaf(Abl[i * 3 + 1], Y[j * 3 + 1], Abl[i * 3 + 2] * Y[j * 3 + 2]));
-            float loc = Alocal ? Alocal[IX6(i, j)] - s : -s;
+            float loc = Alocal[IX6(i, j)] - s;
             A[IX6(i, j)] = Acommon[IX6(i, j)] + qsum(loc, qm);
         }
         float sb = fmaf(Abl[i * 3], t0, fmaf(Abl[i * 3 + 1], t1, Abl[i * 3 + 2] * t2));
@@ -246,6 +184,98 @@ DI void pyramid_rows(v3 u, v3 tx, v3 ty, v3 up, float mu, float* r) {
     r[0] = un + u1; r[1] = un - u1; r[2] = un + u2; r[3] = un - u2;
 }
 
+__device__ __noinline__ float2 sincos_ni(float x) {
+    float s, c;
+    sincosf(x, &s, &c);
+    return make_float2(s, c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// plane-vs-hull collision of all geoms this lane owns (mjc_PlaneConvex restated): oriented-box cull,
+// exhaustive support search over the hull vertices (ties -> lowest index), then up to 3 hull-graph
+// neighbours of the support vertex.  `fr` holds the lane's 4 link frames (level 0 = base): 9 rotation
+// entries (row major, link -> B) and 3 position entries each.
+DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const int* __restrict__ vert_edge,
+                     const int* __restrict__ mesh_edge, int leg, const float* fr, v3 up, float zb, Contacts& C,
+                     StepStats& st) {
+    const int ng = P.ngeom[leg];
+#pragma unroll 1
+    for (int g = 0; g < ng; ++g) {
+        const QgGeomC& G = P.geom[leg][g];
+        const float* f = fr + 12 * G.level;
+        m3 Rk = ldm3(f);
+        v3 pk = ld3(f + 9);
+        v3 ctr = pk + mul(Rk, ld3(G.pos));
+        float zc = zb + dot(up, ctr);
+        m3 RB = matmul(Rk, ldm3(G.R));  // mesh frame -> B
+        v3 dl = tmul(RB, up);           // "up" in the mesh frame
+        float ext = fmaf(fabsf(dl.x), G.half[0], fmaf(fabsf(dl.y), G.half[1], fabsf(dl.z) * G.half[2]));
+        float margin = G.margin;
+        if (zc - ext > margin) continue;  // oriented-box cull (conservative; same contacts as any cull)
+        const float4* __restrict__ vt = verts + G.vert0;
+        const int nvert = G.nvert;
+        int best = 0, best2 = 1;
+        float hbest = 3.0e38f, hbest2 = 3.0e38f;
+        int i = 0;
+        for (; i + 1 < nvert; i += 2) {  // two independent argmin chains (even / odd vertices)
+            float4 v = vt[i], u = vt[i + 1];
+            float h0 = fmaf(dl.x, v.x, fmaf(dl.y, v.y, dl.z * v.z));
+            float h1 = fmaf(dl.x, u.x, fmaf(dl.y, u.y, dl.z * u.z));
+            if (h0 < hbest) { hbest = h0; best = i; }
+            if (h1 < hbest2) { hbest2 = h1; best2 = i + 1; }
+        }
+        if (i < nvert) {
+            float4 v = vt[i];
+            float h0 = fmaf(dl.x, v.x, fmaf(dl.y, v.y, dl.z * v.z));
+            if (h0 < hbest) { hbest = h0; best = i; }
+        }
+        if (hbest2 < hbest || (hbest2 == hbest && best2 < best)) { hbest = hbest2; best = best2; }
+        st.nvert += nvert;
+        if (zc + hbest > margin) continue;
+        // support vertex first, then its hull-graph neighbours (up to 4 contacts per geom)
+        const int* __restrict__ e = mesh_edge + G.edge0 + __ldg(vert_edge + G.vert0 + best);
+        int cnt = 0, cand = best;
+        v3 prev0 = V3(0, 0, 0), prev1 = prev0, prev2 = prev0;
+#pragma unroll 1
+        for (;;) {
+            float4 v = vt[cand];
+            v3 xv = ctr + mul(RB, V3(v.x, v.y, v.z));
+            float dv = zb + dot(up, xv);
+            bool ok = (cnt == 0) || (dv <= margin);
+            if (ok && cnt > 0) {
+                v3 e0 = xv - prev0, e1 = xv - prev1, e2 = xv - prev2;
+                if (dot(e0, e0) < G.tol2) ok = false;
+                if (!P.rule_first) {
+                    if (cnt > 1 && dot(e1, e1) < G.tol2) ok = false;
+                    if (cnt > 2 && dot(e2, e2) < G.tol2) ok = false;
+                }
+            }
+            if (ok) {
+                if (cnt == 0) prev0 = xv; else if (cnt == 1) prev1 = xv; else if (cnt == 2) prev2 = xv;
+                cnt++;
+                if (dv < margin) {  // includemargin: rows are instantiated only for dist < margin
+                    if (C.n < QG_MAXCON_LANE) {
+                        int c = C.n++;
+                        v3 xc = fma3(-0.5f * dv, up, xv);
+                        float r = dv - margin;
+                        float imp = impedance(r, G.d0, G.dmax, G.width, G.mid, G.power);
+                        C.x[c] = xc.x; C.y[c] = xc.y; C.z[c] = xc.z;
+                        C.D[c] = 1.f / fmaxf(1e-15f, (1.f - imp) / imp * G.Rfac);
+                        C.mu[c] = G.mu;
+                        C.Bd[c] = G.B;
+                        C.Kr[c] = G.K * imp * r;
+                        C.lev[c] = G.level;
+                    } else st.overflow++;
+                }
+            }
+            if (cnt >= 4) break;
+            int nb = __ldg(e++);
+            if (nb < 0) break;
+            cand = nb;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 template <bool DEBUG>
 DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const int* __restrict__ vert_edge,
@@ -265,49 +295,64 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
     const v3 gB = tmul(Rb, ld3(P.grav));
     const float zb = S.pb.z - P.plane_z;
 
-    // ---- leg chain: kinematics, collision, inertias, velocity recursion (all in B)
+    // ---- leg kinematics (B coordinates) -> link frames, then collision over the lane's geoms
+    float fr[48];
+    fr[0] = 1.f; fr[1] = 0.f; fr[2] = 0.f; fr[3] = 0.f; fr[4] = 1.f; fr[5] = 0.f; fr[6] = 0.f; fr[7] = 0.f; fr[8] = 1.f;
+    fr[9] = fr[10] = fr[11] = 0.f;
+    {
+        m3 Rk;
+        Rk.r0 = V3(1, 0, 0); Rk.r1 = V3(0, 1, 0); Rk.r2 = V3(0, 0, 1);
+        v3 pk = V3(0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const QgJointC& J = P.joint[leg][k];
+            pk = pk + mul(Rk, ld3(J.pos));
+            m3 Rp = matmul(Rk, ldm3(J.Roff));
+            float2 sc = sincos_ni(S.q[k] - J.q0);
+            const float sn = sc.x, cs = sc.y;
+            Rk.r0 = V3(cs * Rp.r0.x + sn * Rp.r0.y, cs * Rp.r0.y - sn * Rp.r0.x, Rp.r0.z);
+            Rk.r1 = V3(cs * Rp.r1.x + sn * Rp.r1.y, cs * Rp.r1.y - sn * Rp.r1.x, Rp.r1.z);
+            Rk.r2 = V3(cs * Rp.r2.x + sn * Rp.r2.y, cs * Rp.r2.y - sn * Rp.r2.x, Rp.r2.z);
+            float* f = fr + 12 * (k + 1);
+            f[0] = Rk.r0.x; f[1] = Rk.r0.y; f[2] = Rk.r0.z; f[3] = Rk.r1.x; f[4] = Rk.r1.y; f[5] = Rk.r1.z;
+            f[6] = Rk.r2.x; f[7] = Rk.r2.y; f[8] = Rk.r2.z; f[9] = pk.x; f[10] = pk.y; f[11] = pk.z;
+        }
+    }
     C.n = 0;
-    m3 Rk;
-    Rk.r0 = V3(1, 0, 0); Rk.r1 = V3(0, 1, 0); Rk.r2 = V3(0, 0, 1);
-    v3 pk = V3(0, 0, 0);
-    collide_level(P, verts, vert_edge, mesh_edge, leg, 0, P.glev[leg][1], 0, pk, Rk, up, zb, C, st);
+    collide_lane(P, verts, vert_edge, mesh_edge, leg, fr, up, zb, C, st);
 
+    // ---- velocity recursion and inertias along the chain
     v3 sl[3], sa[3];        // joint spatial motion about the B origin: linear p x a, angular a
     v3 ck[3];               // link CoM
     s3 Ik[3];               // link inertia about its CoM, B axes
     v3 Fk[3], Nk[3];        // RNE: inertial force and moment about the B origin
-    v3 omk = S.om, alk = V3(0, 0, 0), apk = -gB;  // angular velocity / acceleration, origin acceleration
+    {
+        v3 omk = S.om, alk = V3(0, 0, 0), apk = -gB, pprev = V3(0, 0, 0);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const QgJointC& J = P.joint[leg][k];
-        v3 pn = pk + mul(Rk, ld3(J.pos));
-        m3 Rp = matmul(Rk, ldm3(J.Roff));
-        float sn, cs;
-        sincosf(S.q[k] - J.q0, &sn, &cs);
-        m3 Rn;  // Rp * Rz(theta)
-        Rn.r0 = V3(cs * Rp.r0.x + sn * Rp.r0.y, cs * Rp.r0.y - sn * Rp.r0.x, Rp.r0.z);
-        Rn.r1 = V3(cs * Rp.r1.x + sn * Rp.r1.y, cs * Rp.r1.y - sn * Rp.r1.x, Rp.r1.z);
-        Rn.r2 = V3(cs * Rp.r2.x + sn * Rp.r2.y, cs * Rp.r2.y - sn * Rp.r2.x, Rp.r2.z);
-        v3 a = col2(Rn);
-        // velocity recursion (classical accelerations, zero generalised acceleration, gravity as base accel)
-        v3 r = pn - pk;
-        apk = apk + cross(alk, r) + cross(omk, cross(omk, r));
-        v3 aq = S.qd[k] * a;
-        alk = alk + cross(omk, aq);
-        omk = omk + aq;
-        pk = pn;
-        Rk = Rn;
-        sa[k] = a;
-        sl[k] = cross(pk, a);
-        v3 dcm = mul(Rk, ld3(J.com));
-        ck[k] = pk + dcm;
-        s3 Ib;
-        Ib.xx = J.I[0]; Ib.yy = J.I[1]; Ib.zz = J.I[2]; Ib.xy = J.I[3]; Ib.xz = J.I[4]; Ib.yz = J.I[5];
-        Ik[k] = rot_sym(Rk, Ib);
-        v3 ac = apk + cross(alk, dcm) + cross(omk, cross(omk, dcm));
-        Fk[k] = J.mass * ac;
-        Nk[k] = mul(Ik[k], alk) + cross(omk, mul(Ik[k], omk)) + cross(ck[k], Fk[k]);
-        collide_level(P, verts, vert_edge, mesh_edge, leg, P.glev[leg][k + 1], P.glev[leg][k + 2], k + 1, pk, Rk, up, zb, C, st);
+        for (int k = 0; k < 3; ++k) {
+            const QgJointC& J = P.joint[leg][k];
+            const float* f = fr + 12 * (k + 1);
+            m3 Rk = ldm3(f);
+            v3 pk = ld3(f + 9);
+            v3 a = col2(Rk);
+            // classical accelerations at zero generalised acceleration, gravity as base acceleration
+            v3 r = pk - pprev;
+            apk = apk + cross(alk, r) + cross(omk, cross(omk, r));
+            v3 aq = S.qd[k] * a;
+            alk = alk + cross(omk, aq);
+            omk = omk + aq;
+            pprev = pk;
+            sa[k] = a;
+            sl[k] = cross(pk, a);
+            v3 dcm = mul(Rk, ld3(J.com));
+            ck[k] = pk + dcm;
+            s3 Ib;
+            Ib.xx = J.I[0]; Ib.yy = J.I[1]; Ib.zz = J.I[2]; Ib.xy = J.I[3]; Ib.xz = J.I[4]; Ib.yz = J.I[5];
+            Ik[k] = rot_sym(Rk, Ib);
+            v3 ac = apk + cross(alk, dcm) + cross(omk, cross(omk, dcm));
+            Fk[k] = J.mass * ac;
+            Nk[k] = mul(Ik[k], alk) + cross(omk, mul(Ik[k], omk)) + cross(ck[k], Fk[k]);
+        }
     }
 
     // ---- backward pass: composite inertias -> M blocks, RNE forces -> bias
@@ -406,14 +451,9 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
         fsl[k] = -J.damping * S.qd[k] - bias_l[k] + tau;
     }
 
-    // ---- unconstrained acceleration
-    float a0b[6], a0l[3];
-    arrow_solve(Mll, Mbl, nullptr, Mbb, fsb, fsl, qm, a0b, a0l);
-
-    // ---- constraint rows: joint limits (own dofs) and pyramidal contacts (table C)
+    // ---- constraint rows: joint limits (own dofs) and pyramidal contacts (table C); jar starts as -aref
     float lsgn[3], lD[3], ljar[3], ljv[3];
     int nlim = 0;
-    float qdb[6] = {vB.x, vB.y, vB.z, S.om.x, S.om.y, S.om.z};
     v3 U[4], W[4];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -434,7 +474,11 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
         }
     }
     const int nc = C.n;
-    twist(qdb, S.qd, sl, sa, U, W);
+    {
+        float qdb[6] = {vB.x, vB.y, vB.z, S.om.x, S.om.y, S.om.z};
+        twist(qdb, S.qd, sl, sa, U, W);
+    }
+#pragma unroll 1
     for (int c = 0; c < nc; ++c) {
         v3 xc = V3(C.x[c], C.y[c], C.z[c]);
         int lev = C.lev[c];
@@ -447,93 +491,192 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
     st.ncon += nc;
     st.nefc += 4 * nc + nlim;
 
-    float ab[6], al[3];       // solver acceleration (B form)
-    float fcb[6], fcl[3];     // constraint force J^T f
+    // ---- phase machine around ONE arrow solve: 0 = unconstrained acceleration (H = M, rhs = qfrc_smooth),
+    //      1 = Newton direction (H = M + J^T D J, rhs = -grad), 2 = implicit integration
+    //      (H = M + h*diag, rhs = qfrc_smooth + qfrc_constraint)
+    float ab[6], al[3], a0b[6], a0l[3], Mab[6], Mal[3];
+    float fcb[6], fcl[3];
+    float Hll[6], Hbl[18], Hc[21], rb[6], rl[3], xb[6], xl[3];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { ab[i] = a0b[i]; fcb[i] = 0.f; }
+    for (int i = 0; i < 6; ++i) { Hll[i] = Mll[i]; rb[i] = fsb[i]; fcb[i] = 0.f; }
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { al[i] = a0l[i]; fcl[i] = 0.f; }
-
-    if (nefc > 0) {
-        float Mab[6], Mal[3];
-        // -- warm start: compare the cost at qacc_warmstart and at qacc_smooth
-        {
-            v3 wlB = tmul(Rb, S.wl);
-            float wb[6] = {wlB.x, wlB.y, wlB.z, S.wa.x, S.wa.y, S.wa.z};
-            float cw = 0.f, cs = 0.f;
-            v3 U2[4], W2[4];
-            twist(wb, S.wj, sl, sa, U, W);
-            twist(a0b, a0l, sl, sa, U2, W2);
+    for (int i = 0; i < 18; ++i) Hbl[i] = Mbl[i];
+#pragma unroll
+    for (int i = 0; i < 21; ++i) Hc[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { rl[i] = fsl[i]; fcl[i] = 0.f; }
+    int phase = 0, iter = 0;
+    float cost_old = 0.f;
+#pragma unroll 1
+    for (;;) {
+        arrow_solve(Hll, Hbl, Hc, Mbb, rb, rl, qm, xb, xl);
+        if (phase == 2) break;
+        bool conv = false;
+        if (phase == 0) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { a0b[i] = xb[i]; ab[i] = xb[i]; Mab[i] = fsb[i]; }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { a0l[i] = xl[i]; al[i] = xl[i]; Mal[i] = fsl[i]; }
+            if (nefc == 0) conv = true;
+            else {
+                // warm start: compare the cost at qacc_warmstart and at qacc_smooth (mj_fwdConstraint)
+                v3 wlB = tmul(Rb, S.wl);
+                float wb[6] = {wlB.x, wlB.y, wlB.z, S.wa.x, S.wa.y, S.wa.z};
+                float cw = 0.f, cs = 0.f;
+                v3 U2[4], W2[4];
+                twist(wb, S.wj, sl, sa, U, W);
+                twist(a0b, a0l, sl, sa, U2, W2);
+#pragma unroll 1
+                for (int c = 0; c < nc; ++c) {
+                    v3 xc = V3(C.x[c], C.y[c], C.z[c]);
+                    int lev = C.lev[c];
+                    float rw[4], rs[4], D = C.D[c];
+                    pyramid_rows(sel4(U, lev) + cross(sel4(W, lev), xc), tx, ty, up, C.mu[c], rw);
+                    pyramid_rows(sel4(U2, lev) + cross(sel4(W2, lev), xc), tx, ty, up, C.mu[c], rs);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float base = C.jar[k][c];
+                        float jw = rw[k] + base, js = rs[k] + base;
+                        C.jar[k][c] = jw;
+                        C.jv[k][c] = js;
+                        cw += (jw < 0.f) ? 0.5f * D * jw * jw : 0.f;
+                        cs += (js < 0.f) ? 0.5f * D * js * js : 0.f;
+                    }
+                }
+                float ljs[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    float jw = fmaf(lsgn[k], S.wj[k], ljar[k]), js = fmaf(lsgn[k], a0l[k], ljar[k]);
+                    ljs[k] = js;
+                    ljar[k] = jw;
+                    cw += (lsgn[k] != 0.f && jw < 0.f) ? 0.5f * lD[k] * jw * jw : 0.f;
+                    cs += (lsgn[k] != 0.f && js < 0.f) ? 0.5f * lD[k] * js * js : 0.f;
+                }
+                float Mwb[6], Mwl[3];
+                arrow_matvec(Mll, Mbl, Mbb, wb, S.wj, qm, Mwb, Mwl);
+                float gl = 0.f, gb = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) gl += 0.5f * (Mwl[k] - fsl[k]) * (S.wj[k] - a0l[k]);
+#pragma unroll
+                for (int r = 0; r < 6; ++r) gb += 0.5f * (Mwb[r] - fsb[r]) * (wb[r] - a0b[r]);
+                float cost_w = qsum(cw + gl, qm) + gb, cost_s = qsum(cs, qm);
+                if (cost_w < cost_s) {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) { ab[i] = wb[i]; Mab[i] = Mwb[i]; }
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) { al[i] = S.wj[i]; Mal[i] = Mwl[i]; }
+                } else {
+#pragma unroll 1
+                    for (int c = 0; c < nc; ++c)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) C.jar[k][c] = C.jv[k][c];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) ljar[k] = ljs[k];
+                }
+            }
+        } else {
+            // ---- (xb, xl) is the Newton direction: exact line search on the convex piecewise quadratic
+            float Mvb[6], Mvl[3];
+            arrow_matvec(Mll, Mbl, Mbb, xb, xl, qm, Mvb, Mvl);
+            float q1l = 0.f, q2l = 0.f, q1b = 0.f, q2b = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { q1l += xl[k] * (Mal[k] - fsl[k]); q2l += 0.5f * xl[k] * Mvl[k]; }
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { q1b += xb[r] * (Mab[r] - fsb[r]); q2b += 0.5f * xb[r] * Mvb[r]; }
+            twist(xb, xl, sl, sa, U, W);
+            // first trial alpha = 1 (the exact minimiser when no row changes state along the step)
+            float e1 = 0.f, e2 = 0.f, z1 = 0.f, z2 = 0.f;
+            int flips = 0;
+#pragma unroll 1
             for (int c = 0; c < nc; ++c) {
                 v3 xc = V3(C.x[c], C.y[c], C.z[c]);
                 int lev = C.lev[c];
-                float rw[4], rs[4], D = C.D[c];
-                pyramid_rows(sel4(U, lev) + cross(sel4(W, lev), xc), tx, ty, up, C.mu[c], rw);
-                pyramid_rows(sel4(U2, lev) + cross(sel4(W2, lev), xc), tx, ty, up, C.mu[c], rs);
+                float rv[4], D = C.D[c];
+                pyramid_rows(sel4(U, lev) + cross(sel4(W, lev), xc), tx, ty, up, C.mu[c], rv);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    float base = C.jar[k][c];
-                    float jw = rw[k] + base, js = rs[k] + base;
-                    C.jar[k][c] = jw;
-                    C.jv[k][c] = js;
-                    cw += (jw < 0.f) ? 0.5f * D * jw * jw : 0.f;
-                    cs += (js < 0.f) ? 0.5f * D * js * js : 0.f;
+                    float jv = rv[k], j0 = C.jar[k][c], j1 = j0 + jv;
+                    C.jv[k][c] = jv;
+                    if (j0 < 0.f) { z1 = fmaf(D * jv, j0, z1); z2 = fmaf(D * jv, jv, z2); }
+                    if (j1 < 0.f) { e1 = fmaf(D * jv, j1, e1); e2 = fmaf(D * jv, jv, e2); }
+                    flips += ((j0 < 0.f) != (j1 < 0.f)) ? 1 : 0;
                 }
             }
-            float ljs[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                float jw = fmaf(lsgn[k], S.wj[k], ljar[k]), js = fmaf(lsgn[k], a0l[k], ljar[k]);
-                ljs[k] = js;
-                ljar[k] = jw;
-                cw += (lsgn[k] != 0.f && jw < 0.f) ? 0.5f * lD[k] * jw * jw : 0.f;
-                cs += (lsgn[k] != 0.f && js < 0.f) ? 0.5f * lD[k] * js * js : 0.f;
+                ljv[k] = lsgn[k] * xl[k];
+                if (lsgn[k] != 0.f) {
+                    float j0 = ljar[k], j1 = j0 + ljv[k];
+                    if (j0 < 0.f) { z1 = fmaf(lD[k] * ljv[k], j0, z1); z2 = fmaf(lD[k] * ljv[k], ljv[k], z2); }
+                    if (j1 < 0.f) { e1 = fmaf(lD[k] * ljv[k], j1, e1); e2 = fmaf(lD[k] * ljv[k], ljv[k], e2); }
+                    flips += ((j0 < 0.f) != (j1 < 0.f)) ? 1 : 0;
+                }
             }
-            arrow_matvec(Mll, Mbl, Mbb, wb, S.wj, qm, Mab, Mal);
-            float gl = 0.f, gb = 0.f;
+            const float q1 = qsum(q1l, qm) + q1b, q2 = qsum(q2l, qm) + q2b;
+            flips = qsumi(flips, qm);
+            st.nls++;
+            float alpha = 1.f;
+            if (flips != 0) {
+                float d10 = qsum(z1, qm) + q1;                         // derivative at 0 (< 0: descent direction)
+                float d1 = qsum(e1, qm) + q1 + 2.f * q2, d2 = qsum(e2, qm) + 2.f * q2;
+                float gtol = 1e-4f * fabsf(d10);
+                float lo = 0.f, hi = -1.f;
+                if (d10 >= 0.f) alpha = 0.f;
+                else {
+#pragma unroll 1
+                    for (int it = 0; it < ls_iter; ++it) {
+                        if (fabsf(d1) < gtol) break;
+                        if (d1 < 0.f) lo = alpha; else hi = alpha;
+                        float an = alpha - d1 / d2;
+                        if (an <= lo || (hi > 0.f && an >= hi)) an = hi > 0.f ? 0.5f * (lo + hi) : 2.f * alpha;
+                        alpha = an;
+                        e1 = 0.f; e2 = 0.f;
+#pragma unroll 1
+                        for (int c = 0; c < nc; ++c) {
+                            float D = C.D[c];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) gl += 0.5f * (Mal[k] - fsl[k]) * (S.wj[k] - a0l[k]);
+                            for (int k = 0; k < 4; ++k) {
+                                float jv = C.jv[k][c], xx = fmaf(alpha, jv, C.jar[k][c]);
+                                if (xx < 0.f) { e1 = fmaf(D * jv, xx, e1); e2 = fmaf(D * jv, jv, e2); }
+                            }
+                        }
 #pragma unroll
-            for (int r = 0; r < 6; ++r) gb += 0.5f * (Mab[r] - fsb[r]) * (wb[r] - a0b[r]);
-            float cost_w = qsum(cw + gl, qm) + gb, cost_s = qsum(cs, qm);
-            if (cost_w < cost_s) {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) ab[i] = wb[i];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) al[i] = S.wj[i];
-            } else {
-                for (int c = 0; c < nc; ++c)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) C.jar[k][c] = C.jv[k][c];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { ljar[k] = ljs[k]; Mal[k] = fsl[k]; }
-#pragma unroll
-                for (int r = 0; r < 6; ++r) Mab[r] = fsb[r];
+                        for (int k = 0; k < 3; ++k) {
+                            float xx = fmaf(alpha, ljv[k], ljar[k]);
+                            if (lsgn[k] != 0.f && xx < 0.f) { e1 = fmaf(lD[k] * ljv[k], xx, e1); e2 = fmaf(lD[k] * ljv[k], ljv[k], e2); }
+                        }
+                        d1 = qsum(e1, qm) + q1 + 2.f * alpha * q2;
+                        d2 = qsum(e2, qm) + 2.f * q2;
+                        st.nls++;
+                    }
+                }
             }
+            if (alpha == 0.f) conv = true;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { ab[r] = fmaf(alpha, xb[r], ab[r]); Mab[r] = fmaf(alpha, Mvb[r], Mab[r]); }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { al[k] = fmaf(alpha, xl[k], al[k]); Mal[k] = fmaf(alpha, Mvl[k], Mal[k]); ljar[k] = fmaf(alpha, ljv[k], ljar[k]); }
+#pragma unroll 1
+            for (int c = 0; c < nc; ++c)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) C.jar[k][c] = fmaf(alpha, C.jv[k][c], C.jar[k][c]);
+            iter++;
+            if (flips == 0) conv = true;  // the quadratic model was exact along the whole step: this is the optimum
         }
 
-        // -- primal Newton iterations
-        float cost_old = 0.f;
-        int iter = 0;
-        for (;;) {
-            float Hll[6], Hbl[18], Hc[21];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) Hll[i] = Mll[i];
-#pragma unroll
-            for (int i = 0; i < 18; ++i) Hbl[i] = Mbl[i];
-#pragma unroll
-            for (int i = 0; i < 21; ++i) Hc[i] = 0.f;
+        float gb[6], gl[3];
+        if (nefc > 0) {
+            // ---- constraint update at the current point: forces, cost, J^T f, gradient
             float cost = 0.f;
             v3 Fb = V3(0, 0, 0), Nb = V3(0, 0, 0);
             float tau[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
             for (int c = 0; c < nc; ++c) {
                 float D = C.D[c], mu = C.mu[c];
                 float j0 = C.jar[0][c], j1 = C.jar[1][c], j2 = C.jar[2][c], j3 = C.jar[3][c];
-                float a0 = j0 < 0.f ? 1.f : 0.f, a1 = j1 < 0.f ? 1.f : 0.f, a2 = j2 < 0.f ? 1.f : 0.f, a3 = j3 < 0.f ? 1.f : 0.f;
-                float na = a0 + a1 + a2 + a3;
-                if (na == 0.f) continue;
-                float f0 = -D * a0 * j0, f1 = -D * a1 * j1, f2 = -D * a2 * j2, f3 = -D * a3 * j3;
-                cost += 0.5f * D * (a0 * j0 * j0 + a1 * j1 * j1 + a2 * j2 * j2 + a3 * j3 * j3);
+                float f0 = j0 < 0.f ? -D * j0 : 0.f, f1 = j1 < 0.f ? -D * j1 : 0.f;
+                float f2 = j2 < 0.f ? -D * j2 : 0.f, f3 = j3 < 0.f ? -D * j3 : 0.f;
+                cost -= 0.5f * (f0 * j0 + f1 * j1 + f2 * j2 + f3 * j3);
                 v3 xc = V3(C.x[c], C.y[c], C.z[c]);
                 int lev = C.lev[c];
                 // force vector in B: sum f_k w_k,  w = up +- mu*ty, up -+ mu*tx
@@ -541,35 +684,97 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                 v3 nn = cross(xc, fc);
                 Fb += fc;
                 Nb += nn;
+                tau[0] += lev >= 1 ? dot(sl[0], fc) + dot(sa[0], nn) : 0.f;
+                tau[1] += lev >= 2 ? dot(sl[1], fc) + dot(sa[1], nn) : 0.f;
+                tau[2] += lev >= 3 ? dot(sl[2], fc) + dot(sa[2], nn) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (lsgn[k] != 0.f && ljar[k] < 0.f) {
+                    float f = -lD[k] * ljar[k];
+                    cost -= 0.5f * f * ljar[k];
+                    tau[k] += lsgn[k] * f;
+                }
+            }
+            float gauss_l = 0.f, gauss_b = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) gauss_l += 0.5f * (Mal[k] - fsl[k]) * (al[k] - a0l[k]);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) gauss_b += 0.5f * (Mab[r] - fsb[r]) * (ab[r] - a0b[r]);
+            cost = qsum(cost + gauss_l, qm) + gauss_b;
+            Fb = qsum(Fb, qm);
+            Nb = qsum(Nb, qm);
+            fcb[0] = Fb.x; fcb[1] = Fb.y; fcb[2] = Fb.z; fcb[3] = Nb.x; fcb[4] = Nb.y; fcb[5] = Nb.z;
+            float g2 = 0.f, g2b = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { fcl[k] = tau[k]; gl[k] = Mal[k] - fsl[k] - tau[k]; g2 += gl[k] * gl[k]; }
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { gb[r] = Mab[r] - fsb[r] - fcb[r]; g2b += gb[r] * gb[r]; }
+            if (phase == 1 && !conv) {
+                float gradient = P.scale * sqrtf(qsum(g2, qm) + g2b);
+                float improvement = P.scale * (cost_old - cost);
+                conv = improvement < P.tol || gradient < P.tol || iter >= max_iter;
+            }
+            cost_old = cost;
+        }
+
+        if (conv) {
+            // ---- next solve: implicit integration  (M + h*diag) qacc+ = qfrc_smooth + qfrc_constraint
+#pragma unroll
+            for (int i = 0; i < 6; ++i) Hll[i] = Mll[i];
+            Hll[0] += h * dimp[0]; Hll[3] += h * dimp[1]; Hll[5] += h * dimp[2];
+#pragma unroll
+            for (int i = 0; i < 18; ++i) Hbl[i] = Mbl[i];
+#pragma unroll
+            for (int i = 0; i < 21; ++i) Hc[i] = 0.f;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { Hc[IX6(r, r)] = (leg == 0) ? h * P.base_damp[r] : 0.f; rb[r] = fsb[r] + fcb[r]; }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) rl[k] = fsl[k] + fcl[k];
+            phase = 2;
+        } else {
+            // ---- next solve: Newton direction.  H = M + J^T D J over the active rows
+#pragma unroll
+            for (int i = 0; i < 6; ++i) Hll[i] = Mll[i];
+#pragma unroll
+            for (int i = 0; i < 18; ++i) Hbl[i] = Mbl[i];
+#pragma unroll
+            for (int i = 0; i < 21; ++i) Hc[i] = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < nc; ++c) {
+                float D = C.D[c], mu = C.mu[c];
+                float a0 = C.jar[0][c] < 0.f ? 1.f : 0.f, a1 = C.jar[1][c] < 0.f ? 1.f : 0.f;
+                float a2 = C.jar[2][c] < 0.f ? 1.f : 0.f, a3 = C.jar[3][c] < 0.f ? 1.f : 0.f;
+                float na = a0 + a1 + a2 + a3;
+                if (na == 0.f) continue;
+                v3 xc = V3(C.x[c], C.y[c], C.z[c]);
+                int lev = C.lev[c];
                 // Jacobian columns of the leg joints at the contact point (zero above the contact's link)
                 v3 jc0 = lev >= 1 ? sl[0] + cross(sa[0], xc) : V3(0, 0, 0);
                 v3 jc1 = lev >= 2 ? sl[1] + cross(sa[1], xc) : V3(0, 0, 0);
                 v3 jc2 = lev >= 3 ? sl[2] + cross(sa[2], xc) : V3(0, 0, 0);
-                tau[0] += dot(jc0, fc); tau[1] += dot(jc1, fc); tau[2] += dot(jc2, fc);
-                // W = D * sum_active w w^T  in the (tx, ty, up) basis: diag/offdiag coefficients
-                float sy = a0 + a1, sx = a2 + a3;     // rows touching ty / tx
-                float dy = a0 - a1, dx = a3 - a2;     // signed: w0=up+mu ty, w1=up-mu ty, w2=up-mu tx, w3=up+mu tx
+                // W = D * sum_active w w^T in the (tx, ty, up) basis; w0=up+mu ty, w1=up-mu ty, w2=up-mu tx, w3=up+mu tx
+                float sy = a0 + a1, sx = a2 + a3, dy = a0 - a1, dx = a3 - a2;
                 float wuu = D * na, wyy = D * mu * mu * sy, wxx = D * mu * mu * sx, wuy = D * mu * dy, wux = D * mu * dx;
-                // W v = wuu up(up.v) + wyy ty(ty.v) + wxx tx(tx.v) + wuy (up(ty.v)+ty(up.v)) + wux (up(tx.v)+tx(up.v))
 #define WMUL(v, out)                                                                                   \
     {                                                                                                  \
         float pu = dot(up, v), py = dot(ty, v), px = dot(tx, v);                                       \
         out = fma3(wuu * pu + wuy * py + wux * px, up, fma3(wyy * py + wuy * pu, ty, (wxx * px + wux * pu) * tx)); \
     }
-                v3 Wx, Wy, Wz, q0, q1, q2;
+                v3 Wx, Wy, Wz, q0, q1v, q2v;
                 WMUL(V3(1, 0, 0), Wx);
                 WMUL(V3(0, 1, 0), Wy);
                 WMUL(V3(0, 0, 1), Wz);
                 WMUL(jc0, q0);
-                WMUL(jc1, q1);
-                WMUL(jc2, q2);
+                WMUL(jc1, q1v);
+                WMUL(jc2, q2v);
 #undef WMUL
-                Hll[0] += dot(jc0, q0); Hll[1] += dot(jc0, q1); Hll[2] += dot(jc0, q2);
-                Hll[3] += dot(jc1, q1); Hll[4] += dot(jc1, q2); Hll[5] += dot(jc2, q2);
-                v3 x0 = cross(xc, q0), x1 = cross(xc, q1), x2 = cross(xc, q2);
-                Hbl[0] += q0.x; Hbl[1] += q1.x; Hbl[2] += q2.x;
-                Hbl[3] += q0.y; Hbl[4] += q1.y; Hbl[5] += q2.y;
-                Hbl[6] += q0.z; Hbl[7] += q1.z; Hbl[8] += q2.z;
+                Hll[0] += dot(jc0, q0); Hll[1] += dot(jc0, q1v); Hll[2] += dot(jc0, q2v);
+                Hll[3] += dot(jc1, q1v); Hll[4] += dot(jc1, q2v); Hll[5] += dot(jc2, q2v);
+                v3 x0 = cross(xc, q0), x1 = cross(xc, q1v), x2 = cross(xc, q2v);
+                Hbl[0] += q0.x; Hbl[1] += q1v.x; Hbl[2] += q2v.x;
+                Hbl[3] += q0.y; Hbl[4] += q1v.y; Hbl[5] += q2v.y;
+                Hbl[6] += q0.z; Hbl[7] += q1v.z; Hbl[8] += q2v.z;
                 Hbl[9] += x0.x; Hbl[10] += x1.x; Hbl[11] += x2.x;
                 Hbl[12] += x0.y; Hbl[13] += x1.y; Hbl[14] += x2.y;
                 Hbl[15] += x0.z; Hbl[16] += x1.z; Hbl[17] += x2.z;
@@ -586,104 +791,16 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                 Hc[IX6(5, 3)] += r5.x; Hc[IX6(5, 4)] += r5.y; Hc[IX6(5, 5)] += r5.z;
             }
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (lsgn[k] != 0.f && ljar[k] < 0.f) {
-                    float f = -lD[k] * ljar[k];
-                    cost += 0.5f * lD[k] * ljar[k] * ljar[k];
-                    tau[k] += lsgn[k] * f;
-                    Hll[k == 0 ? 0 : (k == 1 ? 3 : 5)] += lD[k];
-                }
-            }
-            float gauss_l = 0.f, gauss_b = 0.f;
+            for (int k = 0; k < 3; ++k)
+                if (lsgn[k] != 0.f && ljar[k] < 0.f) Hll[k == 0 ? 0 : (k == 1 ? 3 : 5)] += lD[k];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) gauss_l += 0.5f * (Mal[k] - fsl[k]) * (al[k] - a0l[k]);
+            for (int r = 0; r < 6; ++r) rb[r] = -gb[r];
 #pragma unroll
-            for (int r = 0; r < 6; ++r) gauss_b += 0.5f * (Mab[r] - fsb[r]) * (ab[r] - a0b[r]);
-            cost = qsum(cost + gauss_l, qm) + gauss_b;
-            Fb = qsum(Fb, qm);
-            Nb = qsum(Nb, qm);
-            fcb[0] = Fb.x; fcb[1] = Fb.y; fcb[2] = Fb.z; fcb[3] = Nb.x; fcb[4] = Nb.y; fcb[5] = Nb.z;
-            float gb[6], gl[3], g2 = 0.f, g2b = 0.f;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { fcl[k] = tau[k]; gl[k] = Mal[k] - fsl[k] - tau[k]; g2 += gl[k] * gl[k]; }
-#pragma unroll
-            for (int r = 0; r < 6; ++r) { gb[r] = Mab[r] - fsb[r] - fcb[r]; g2b += gb[r] * gb[r]; }
-            if (iter > 0) {
-                float gradient = P.scale * sqrtf(qsum(g2, qm) + g2b);
-                float improvement = P.scale * (cost_old - cost);
-                if (improvement < P.tol || gradient < P.tol || iter >= max_iter) break;
-            }
-            // Newton direction
-            float sb[6], sv[3], nb6[6], nl3[3];
-#pragma unroll
-            for (int r = 0; r < 6; ++r) nb6[r] = -gb[r];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) nl3[k] = -gl[k];
-            arrow_solve(Hll, Hbl, Hc, Mbb, nb6, nl3, qm, sb, sv);
-            float Mvb[6], Mvl[3];
-            arrow_matvec(Mll, Mbl, Mbb, sb, sv, qm, Mvb, Mvl);
-            float q1l = 0.f, q2l = 0.f, q1b = 0.f, q2b = 0.f, snl = 0.f, snb = 0.f;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { q1l += sv[k] * (Mal[k] - fsl[k]); q2l += 0.5f * sv[k] * Mvl[k]; snl += sv[k] * sv[k]; }
-#pragma unroll
-            for (int r = 0; r < 6; ++r) { q1b += sb[r] * (Mab[r] - fsb[r]); q2b += 0.5f * sb[r] * Mvb[r]; snb += sb[r] * sb[r]; }
-            float q1 = qsum(q1l, qm) + q1b, q2 = qsum(q2l, qm) + q2b, snorm = sqrtf(qsum(snl, qm) + snb);
-            if (snorm < 1e-15f) break;
-            twist(sb, sv, sl, sa, U, W);
-            for (int c = 0; c < nc; ++c) {
-                v3 xc = V3(C.x[c], C.y[c], C.z[c]);
-                int lev = C.lev[c];
-                float rv[4];
-                pyramid_rows(sel4(U, lev) + cross(sel4(W, lev), xc), tx, ty, up, C.mu[c], rv);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) C.jv[k][c] = rv[k];
-            }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) ljv[k] = lsgn[k] * sv[k];
-            // exact line search on the convex piecewise-quadratic: safeguarded Newton on the derivative
-            float alpha = 0.f, lo = 0.f, hi = -1.f, d1 = 0.f, d2 = 0.f;
-            float gtol = fmaxf(P.tol * 0.01f * snorm / P.scale, 1e-6f * fabsf(q1));
-            for (int it = 0; it <= ls_iter; ++it) {
-                float e1 = 0.f, e2 = 0.f;
-                for (int c = 0; c < nc; ++c) {
-                    float D = C.D[c];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        float jv = C.jv[k][c], xx = fmaf(alpha, jv, C.jar[k][c]);
-                        if (xx < 0.f) { e1 = fmaf(D * jv, xx, e1); e2 = fmaf(D * jv, jv, e2); }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    float xx = fmaf(alpha, ljv[k], ljar[k]);
-                    if (lsgn[k] != 0.f && xx < 0.f) { e1 = fmaf(lD[k] * ljv[k], xx, e1); e2 = fmaf(lD[k] * ljv[k], ljv[k], e2); }
-                }
-                d1 = qsum(e1, qm) + q1 + 2.f * alpha * q2;
-                d2 = qsum(e2, qm) + 2.f * q2;
-                st.nls++;
-                if (it == 0) { if (d1 >= 0.f) break; }
-                else {
-                    if (fabsf(d1) < gtol) break;
-                    if (d1 < 0.f) lo = alpha; else hi = alpha;
-                }
-                if (it == ls_iter) break;
-                float an = alpha - d1 / d2;
-                if (an <= lo || (hi > 0.f && an >= hi)) an = hi > 0.f ? 0.5f * (lo + hi) : 2.f * (lo > 0.f ? lo : 1e-3f);
-                alpha = an;
-            }
-            if (alpha == 0.f) break;
-#pragma unroll
-            for (int r = 0; r < 6; ++r) { ab[r] = fmaf(alpha, sb[r], ab[r]); Mab[r] = fmaf(alpha, Mvb[r], Mab[r]); }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { al[k] = fmaf(alpha, sv[k], al[k]); Mal[k] = fmaf(alpha, Mvl[k], Mal[k]); ljar[k] = fmaf(alpha, ljv[k], ljar[k]); }
-            for (int c = 0; c < nc; ++c)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) C.jar[k][c] = fmaf(alpha, C.jv[k][c], C.jar[k][c]);
-            cost_old = cost;
-            iter++;
+            for (int k = 0; k < 3; ++k) rl[k] = -gl[k];
+            phase = 1;
         }
-        st.niter += (leg == 0) ? iter : 0;
     }
+    st.niter += (leg == 0) ? iter : 0;
 
     // ---- sensors of this forward pass (pre-integration state, solver qacc)
     if (want_sensors) {
@@ -737,45 +854,30 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
         }
     }
 
-    // ---- integrate: (M + h*diag) qacc+ = qfrc_smooth + qfrc_constraint ; semi-implicit update
-    {
-        float Hll[6], Hb[21], rb[6], rl[3], xb[6], xl[3];
+    // ---- semi-implicit update with qacc+ = (xb, xl); warm start for the next step = solver acceleration
+    S.wl = mul(Rb, V3(ab[0], ab[1], ab[2]));
+    S.wa = V3(ab[3], ab[4], ab[5]);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) Hll[i] = Mll[i];
-        Hll[0] += h * dimp[0]; Hll[3] += h * dimp[1]; Hll[5] += h * dimp[2];
-#pragma unroll
-        for (int i = 0; i < 21; ++i) Hb[i] = Mbb[i];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) { Hb[IX6(r, r)] += h * P.base_damp[r]; rb[r] = fsb[r] + fcb[r]; }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) rl[k] = fsl[k] + fcl[k];
-        arrow_solve(Hll, Mbl, nullptr, Hb, rb, rl, qm, xb, xl);
-        // warm start for the next step = this step's solver acceleration (world form)
-        S.wl = mul(Rb, V3(ab[0], ab[1], ab[2]));
-        S.wa = V3(ab[3], ab[4], ab[5]);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            S.wj[k] = al[k];
-            S.act[k] = fmaf(act_dot[k], P.joint[leg][k].act_fac, S.act[k]);
-            S.qd[k] = fmaf(h, xl[k], S.qd[k]);
-            S.q[k] = fmaf(h, S.qd[k], S.q[k]);
-        }
-        v3 vBn = fma3(h, V3(xb[0], xb[1], xb[2]), vB);
-        S.vw = mul(Rb, vBn);
-        S.om = fma3(h, V3(xb[3], xb[4], xb[5]), S.om);
-        S.pb = fma3(h, S.vw, S.pb);
-        float wn = sqrtf(dot(S.om, S.om));
-        float rw = 1.f, rx = 0.f, ry = 0.f, rz = 0.f;
-        if (wn > 1e-15f) {
-            float sn, cs;
-            sincosf(0.5f * h * wn, &sn, &cs);
-            float s = sn / wn;
-            rw = cs; rx = S.om.x * s; ry = S.om.y * s; rz = S.om.z * s;
-        }
-        S.qw = w * rw - x * rx - y * ry - z * rz;
-        S.qx = w * rx + x * rw + y * rz - z * ry;
-        S.qy = w * ry - x * rz + y * rw + z * rx;
-        S.qz = w * rz + x * ry - y * rx + z * rw;
-        S.time += P.timestep_d;
+    for (int k = 0; k < 3; ++k) {
+        S.wj[k] = al[k];
+        S.act[k] = fmaf(act_dot[k], P.joint[leg][k].act_fac, S.act[k]);
+        S.qd[k] = fmaf(h, xl[k], S.qd[k]);
+        S.q[k] = fmaf(h, S.qd[k], S.q[k]);
     }
+    v3 vBn = fma3(h, V3(xb[0], xb[1], xb[2]), vB);
+    S.vw = mul(Rb, vBn);
+    S.om = fma3(h, V3(xb[3], xb[4], xb[5]), S.om);
+    S.pb = fma3(h, S.vw, S.pb);
+    float wn = sqrtf(dot(S.om, S.om));
+    float rw = 1.f, rx = 0.f, ry = 0.f, rz = 0.f;
+    if (wn > 1e-15f) {
+        float2 sc = sincos_ni(0.5f * h * wn);
+        float s = sc.x / wn;
+        rw = sc.y; rx = S.om.x * s; ry = S.om.y * s; rz = S.om.z * s;
+    }
+    S.qw = w * rw - x * rx - y * ry - z * rz;
+    S.qx = w * rx + x * rw + y * rz - z * ry;
+    S.qy = w * ry - x * rz + y * rw + z * rx;
+    S.qz = w * rz + x * ry - y * rx + z * rw;
+    S.time += P.timestep_d;
 }
