@@ -298,6 +298,27 @@ extern "C" int qg_model_load(const void* blob, size_t nbytes, qg_model** out) {
     m->vert_edge = I("mesh_vert_edge");
     m->mesh_edge = I("mesh_edge");
     c.nvert = nvert;
+    if (nmesh > QG_MAXMESH) BADMODEL("too many meshes (%d > %d)", nmesh, QG_MAXMESH);
+    // support-search start table: exhaustive argmin at the centre direction of every cube-map cell
+    for (int me = 0; me < nmesh; ++me) {
+        int v0 = I("mesh_vertadr")[me], vn = I("mesh_vertnum")[me];
+        for (int face = 0; face < 6; ++face)
+            for (int iu = 0; iu < QG_DIRRES; ++iu)
+                for (int iv = 0; iv < QG_DIRRES; ++iv) {
+                    int a = face >> 1, o0 = (a + 1) % 3, o1 = (a + 2) % 3;
+                    double d[3];
+                    d[a] = (face & 1) ? 1.0 : -1.0;
+                    d[o0] = (iu + 0.5) * 2.0 / QG_DIRRES - 1.0;
+                    d[o1] = (iv + 0.5) * 2.0 / QG_DIRRES - 1.0;
+                    int best = 0;
+                    double hb = 1e300;
+                    for (int i = 0; i < vn; ++i) {
+                        double hh = d[0] * mv[3 * (v0 + i)] + d[1] * mv[3 * (v0 + i) + 1] + d[2] * mv[3 * (v0 + i) + 2];
+                        if (hh < hb) { hb = hh; best = i; }
+                    }
+                    c.dir_start[me][(face * QG_DIRRES + iu) * QG_DIRRES + iv] = (unsigned short)best;
+                }
+    }
     // geoms: leg geoms to their lane, base geoms to the lane with the fewest geoms so far
     std::vector<int> lane_of(ngeom), level_of(ngeom);
     int count[QG_NLEG] = {0, 0, 0, 0};
@@ -349,6 +370,7 @@ extern "C" int qg_model_load(const void* blob, size_t nbytes, qg_model** out) {
                 G.vert0 = v0; G.nvert = vn;
                 G.edge0 = I("mesh_edgeadr")[me];
                 G.level = lev;
+                G.mesh = me;
             }
         }
         c.glev[l][QG_NLINK + 1] = n;

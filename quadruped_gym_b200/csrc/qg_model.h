@@ -15,6 +15,9 @@
 #define QG_MAXCON_LANE 24   // contacts one lane can hold
 #define QG_MAXVERT 1024     // unique hull vertices over all meshes (float4 each in shared memory)
 #define QG_MAX_TERMS_ 16
+#define QG_MAXMESH 8
+#define QG_DIRRES 4          // support-search start table: cube map, 6 faces x QG_DIRRES^2 cells per mesh
+#define QG_DIRCELLS (6 * QG_DIRRES * QG_DIRRES)
 
 // state planes: float4 S[plane * N + env]
 #define QG_PL_POS 0     // base position (world)            x y z _
@@ -58,6 +61,7 @@ struct QgGeomC {
     int vert0, nvert;  // slice of the vertex table
     int edge0;         // offset of this mesh' edge lists in mesh_edge (global memory)
     int level;         // 0 = base, 1..3 = leg link
+    int mesh;          // mesh id (row of dir_start)
 };
 
 struct alignas(16) QgModelC {
@@ -76,6 +80,9 @@ struct alignas(16) QgModelC {
     QgGeomC geom[QG_NLEG][QG_MAXGEOM_LANE];
     int nvert;             // hull vertices over all meshes (float4 table staged in shared memory)
     int pad_;
+    // hill-climb start vertex (local id) for the support search, indexed by the cube-map cell of the
+    // search direction in the mesh frame
+    unsigned short dir_start[QG_MAXMESH][QG_DIRCELLS];
 };
 
 struct QgStepOpts {

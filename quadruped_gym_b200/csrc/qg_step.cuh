@@ -192,7 +192,7 @@ __device__ __noinline__ float2 sincos_ni(float x) {
 
 // ---------------------------------------------------------------------------------------------
 // plane-vs-hull collision of all geoms this lane owns (mjc_PlaneConvex restated): oriented-box cull,
-// exhaustive support search over the hull vertices (ties -> lowest index), then up to 3 hull-graph
+// hill-climbing support search on the hull graph (exact for a convex hull), then up to 3 hull-graph
 // neighbours of the support vertex.  `fr` holds the lane's 4 link frames (level 0 = base): 9 rotation
 // entries (row major, link -> B) and 3 position entries each.
 DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const int* __restrict__ vert_edge,
@@ -213,27 +213,50 @@ DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const 
         float margin = G.margin;
         if (zc - ext > margin) continue;  // oriented-box cull (conservative; same contacts as any cull)
         const float4* __restrict__ vt = verts + G.vert0;
-        const int nvert = G.nvert;
-        int best = 0, best2 = 1;
-        float hbest = 3.0e38f, hbest2 = 3.0e38f;
-        int i = 0;
-        for (; i + 1 < nvert; i += 2) {  // two independent argmin chains (even / odd vertices)
-            float4 v = vt[i], u = vt[i + 1];
-            float h0 = fmaf(dl.x, v.x, fmaf(dl.y, v.y, dl.z * v.z));
-            float h1 = fmaf(dl.x, u.x, fmaf(dl.y, u.y, dl.z * u.z));
-            if (h0 < hbest) { hbest = h0; best = i; }
-            if (h1 < hbest2) { hbest2 = h1; best2 = i + 1; }
+        const int* __restrict__ ve = vert_edge + G.vert0;
+        const int* __restrict__ el = mesh_edge + G.edge0;
+        // support vertex along -up: start from the cube-map cell of the direction, then hill-climb on the
+        // hull graph (a vertex of a convex polytope that is not the minimiser has a strictly lower neighbour)
+        int best;
+        {
+            float ax = fabsf(dl.x), ay = fabsf(dl.y), az = fabsf(dl.z);
+            int a = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
+            float dm = a == 0 ? dl.x : (a == 1 ? dl.y : dl.z);
+            float du = a == 0 ? dl.y : (a == 1 ? dl.z : dl.x);
+            float dw = a == 0 ? dl.z : (a == 1 ? dl.x : dl.y);
+            float inv = 1.f / fmaxf(fabsf(dm), 1e-20f);
+            int iu = min(QG_DIRRES - 1, max(0, (int)((du * inv + 1.f) * (0.5f * QG_DIRRES))));
+            int iv = min(QG_DIRRES - 1, max(0, (int)((dw * inv + 1.f) * (0.5f * QG_DIRRES))));
+            best = P.dir_start[G.mesh][((2 * a + (dm > 0.f ? 1 : 0)) * QG_DIRRES + iu) * QG_DIRRES + iv];
         }
-        if (i < nvert) {
-            float4 v = vt[i];
-            float h0 = fmaf(dl.x, v.x, fmaf(dl.y, v.y, dl.z * v.z));
-            if (h0 < hbest) { hbest = h0; best = i; }
+        float hbest;
+        {
+            float4 v = vt[best];
+            hbest = fmaf(dl.x, v.x, fmaf(dl.y, v.y, dl.z * v.z));
         }
-        if (hbest2 < hbest || (hbest2 == hbest && best2 < best)) { hbest = hbest2; best = best2; }
-        st.nvert += nvert;
+        int nev = 1;
+#pragma unroll 1
+        for (;;) {
+            const int* __restrict__ e = el + __ldg(ve + best);
+            int nxt = -1;
+            float hn = hbest;
+#pragma unroll 1
+            for (;;) {
+                int nb = __ldg(e++);
+                if (nb < 0) break;
+                float4 v = vt[nb];
+                float hh = fmaf(dl.x, v.x, fmaf(dl.y, v.y, dl.z * v.z));
+                nev++;
+                if (hh < hn) { hn = hh; nxt = nb; }
+            }
+            if (nxt < 0) break;
+            best = nxt;
+            hbest = hn;
+        }
+        st.nvert += nev;
         if (zc + hbest > margin) continue;
         // support vertex first, then its hull-graph neighbours (up to 4 contacts per geom)
-        const int* __restrict__ e = mesh_edge + G.edge0 + __ldg(vert_edge + G.vert0 + best);
+        const int* __restrict__ e = el + __ldg(ve + best);
         int cnt = 0, cand = best;
         v3 prev0 = V3(0, 0, 0), prev1 = prev0, prev2 = prev0;
 #pragma unroll 1
