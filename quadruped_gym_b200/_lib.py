@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libquadgym.so")
+LIB_PATH = os.environ.get("QG_LIB", os.path.join(_HERE, "libquadgym.so"))  # QG_LIB: tuning builds only
 
 QG_NQ, QG_NV, QG_NU, QG_NSENSORDATA, QG_MAX_TERMS = 19, 18, 12, 33, 16
 

@@ -32,8 +32,9 @@ static int fail(int code, const char* fmt, ...) {
 struct qg_model {
     QgModelC c;
     std::vector<float> verts;     // xyz_ per hull vertex
-    std::vector<int> vert_edge;   // per vertex: start of neighbour list relative to the mesh' edge0
-    std::vector<int> mesh_edge;
+    std::vector<int> vert_adj;    // per vertex: start of its neighbour list in int4 units, relative to the mesh' edge0
+    std::vector<int> adj;         // neighbour lists (local vertex ids), -1 terminated and padded to groups of 4
+    std::vector<int> vert_cadj, cadj;  // same for the polytope-edge graph (hill climbing)
     int sizes[8];
     double timestep;
 };
@@ -42,7 +43,8 @@ struct qg_batch {
     int n, device;
     QgModelC* d_model;
     float4* d_verts;
-    int *d_vert_edge, *d_mesh_edge;
+    int *d_vert_adj, *d_vert_cadj;
+    int4 *d_adj4, *d_cadj4;
     float4* d_state;
     QgCounters* d_ctr;
     QgStepOpts opts;
@@ -295,8 +297,41 @@ extern "C" int qg_model_load(const void* blob, size_t nbytes, qg_model** out) {
         m->verts[4 * i] = (float)mv[3 * i]; m->verts[4 * i + 1] = (float)mv[3 * i + 1]; m->verts[4 * i + 2] = (float)mv[3 * i + 2];
         m->verts[4 * i + 3] = 0.f;
     }
-    m->vert_edge = I("mesh_vert_edge");
-    m->mesh_edge = I("mesh_edge");
+    // neighbour lists re-packed per mesh: each list is -1 terminated and padded with -1 to a multiple of 4 ints.
+    // Two graphs: the full hull triangulation (extra plane-mesh contacts enumerate its neighbour order) and the
+    // polytope-edge graph without diagonals of coplanar facets (support-search hill climbing).
+    std::vector<int> mesh_adj0(nmesh, 0), mesh_cadj0(nmesh, 0);  // start of each mesh' lists in int4 units
+    auto pack_adj = [&](const std::vector<int>& ve, const std::vector<int>& ed, const std::vector<int>& eadr,
+                        std::vector<int>& vert_out, std::vector<int>& adj_out, std::vector<int>& mesh0) -> bool {
+        vert_out.assign(nvert, 0);
+        for (int me = 0; me < nmesh; ++me) {
+            int v0 = I("mesh_vertadr")[me], vn = I("mesh_vertnum")[me], e0 = eadr[me];
+            mesh0[me] = (int)adj_out.size() / 4;
+            for (int v = 0; v < vn; ++v) {
+                vert_out[v0 + v] = (int)adj_out.size() / 4 - mesh0[me];
+                size_t i = (size_t)e0 + ve[v0 + v];
+                while (i < ed.size() && ed[i] >= 0) {
+                    if (ed[i] >= vn) return false;
+                    adj_out.push_back(ed[i++]);
+                }
+                adj_out.push_back(-1);
+                while (adj_out.size() % 4) adj_out.push_back(-1);
+            }
+        }
+        return true;
+    };
+    if (!pack_adj(I("mesh_vert_edge"), I("mesh_edge"), I("mesh_edgeadr"), m->vert_adj, m->adj, mesh_adj0))
+        BADMODEL("mesh_edge: neighbour index out of range");
+    if (B.i.count("mesh_cedge") && B.i.count("mesh_vert_cedge") && B.i.count("mesh_cedgeadr")) {
+        CHECK_LEN(I("mesh_vert_cedge"), nvert, "mesh_vert_cedge");
+        CHECK_LEN(I("mesh_cedgeadr"), nmesh, "mesh_cedgeadr");
+        if (!pack_adj(I("mesh_vert_cedge"), I("mesh_cedge"), I("mesh_cedgeadr"), m->vert_cadj, m->cadj, mesh_cadj0))
+            BADMODEL("mesh_cedge: neighbour index out of range");
+    } else {  // older blobs: climb on the full triangulation
+        m->vert_cadj = m->vert_adj;
+        m->cadj = m->adj;
+        mesh_cadj0 = mesh_adj0;
+    }
     c.nvert = nvert;
     if (nmesh > QG_MAXMESH) BADMODEL("too many meshes (%d > %d)", nmesh, QG_MAXMESH);
     // support-search start table: exhaustive argmin at the centre direction of every cube-map cell
@@ -368,7 +403,8 @@ extern "C" int qg_model_load(const void* blob, size_t nbytes, qg_model** out) {
                 double rb = F("geom_rbound")[g];
                 G.tol2 = (float)(0.09 * rb * rb);
                 G.vert0 = v0; G.nvert = vn;
-                G.edge0 = I("mesh_edgeadr")[me];
+                G.edge0 = mesh_adj0[me];
+                G.cedge0 = mesh_cadj0[me];
                 G.level = lev;
                 G.mesh = me;
             }
@@ -422,17 +458,21 @@ extern "C" int qg_batch_create(const qg_model* m, int n_envs, int device, qg_bat
     size_t nv = m->verts.size() / 4;
     CUDA_OK(cudaMalloc(&b->d_model, sizeof(QgModelC)));
     CUDA_OK(cudaMalloc(&b->d_verts, sizeof(float4) * (nv ? nv : 1)));
-    CUDA_OK(cudaMalloc(&b->d_vert_edge, sizeof(int) * (nv ? nv : 1)));
-    CUDA_OK(cudaMalloc(&b->d_mesh_edge, sizeof(int) * (m->mesh_edge.size() ? m->mesh_edge.size() : 1)));
+    CUDA_OK(cudaMalloc(&b->d_vert_adj, sizeof(int) * (nv ? nv : 1)));
+    CUDA_OK(cudaMalloc(&b->d_adj4, sizeof(int) * (m->adj.size() ? m->adj.size() : 4)));
+    CUDA_OK(cudaMalloc(&b->d_vert_cadj, sizeof(int) * (nv ? nv : 1)));
+    CUDA_OK(cudaMalloc(&b->d_cadj4, sizeof(int) * (m->cadj.size() ? m->cadj.size() : 4)));
     CUDA_OK(cudaMalloc(&b->d_state, sizeof(float4) * (size_t)QG_NPLANE * n_envs));
     CUDA_OK(cudaMalloc(&b->d_ctr, sizeof(QgCounters)));
     CUDA_OK(cudaMemcpy(b->d_model, &m->c, sizeof(QgModelC), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(b->d_verts, m->verts.data(), sizeof(float) * m->verts.size(), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(b->d_vert_edge, m->vert_edge.data(), sizeof(int) * m->vert_edge.size(), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(b->d_mesh_edge, m->mesh_edge.data(), sizeof(int) * m->mesh_edge.size(), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(b->d_vert_adj, m->vert_adj.data(), sizeof(int) * m->vert_adj.size(), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(b->d_adj4, m->adj.data(), sizeof(int) * m->adj.size(), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(b->d_vert_cadj, m->vert_cadj.data(), sizeof(int) * m->vert_cadj.size(), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(b->d_cadj4, m->cadj.data(), sizeof(int) * m->cadj.size(), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemset(b->d_state, 0, sizeof(float4) * (size_t)QG_NPLANE * n_envs));
     CUDA_OK(cudaMemset(b->d_ctr, 0, sizeof(QgCounters)));
-    b->smem = ((sizeof(QgModelC) + 15) & ~size_t(15)) + sizeof(float4) * nv;
+    b->smem = ((sizeof(QgModelC) + 15) & ~size_t(15)) + sizeof(float4) * nv + sizeof(float) * QG_QR_SLOTS * 32 * (QG_BLOCK / 32);
     CUDA_OK(cudaFuncSetAttribute(qg_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
     CUDA_OK(cudaFuncSetAttribute(qg_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
     *out = b;
@@ -445,7 +485,7 @@ extern "C" int qg_batch_create(const qg_model* m, int n_envs, int device, qg_bat
 extern "C" void qg_batch_destroy(qg_batch* b) {
     if (!b) return;
     cudaSetDevice(b->device);
-    cudaFree(b->d_model); cudaFree(b->d_verts); cudaFree(b->d_vert_edge); cudaFree(b->d_mesh_edge);
+    cudaFree(b->d_model); cudaFree(b->d_verts); cudaFree(b->d_vert_adj); cudaFree(b->d_adj4); cudaFree(b->d_vert_cadj); cudaFree(b->d_cadj4);
     cudaFree(b->d_state); cudaFree(b->d_ctr);
     if (b->h_act) cudaFreeHost(b->h_act);
     if (b->h_obs) cudaFreeHost(b->h_obs);
@@ -501,7 +541,7 @@ extern "C" int qg_reset(qg_batch* b, const uint8_t* mask_dev, uint64_t seed, int
 template <bool DEBUG>
 static int launch_step(qg_batch* b, const float* action, int clip, int frame_skip, float* obs, float* reward, float* terms,
                        unsigned char* terminated, float* terminal_obs, QgDebugOut dbg, cudaStream_t st) {
-    qg_step_kernel<DEBUG><<<nblocks(b->n), QG_BLOCK, b->smem, st>>>(b->d_model, b->d_verts, b->d_vert_edge, b->d_mesh_edge,
+    qg_step_kernel<DEBUG><<<nblocks(b->n), QG_BLOCK, b->smem, st>>>(b->d_model, b->d_verts, b->d_vert_adj, b->d_adj4, b->d_vert_cadj, b->d_cadj4,
                                                                      b->d_state, b->n, action, clip, frame_skip, obs, reward,
                                                                      terms, terminated, terminal_obs, b->opts, b->d_ctr, dbg);
     g_launches++;

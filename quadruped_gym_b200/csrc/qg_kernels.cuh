@@ -6,9 +6,20 @@
 //   :178 termination any, plus the SB3-style auto-reset that SubprocVecEnv performs around it
 //   (/root/reference/src/train_quadruped.py:50) and mj_resetData + default ctrl (quadruped.py:120-124).
 #pragma once
+#ifndef QG_BLOCKSYNC
+#define QG_BLOCKSYNC 2
+#endif
 #include "qg_step.cuh"
 
-#define QG_BLOCK 128
+#ifndef QG_BLOCK
+#define QG_BLOCK 256
+#endif
+#ifndef QG_MINBLOCKS
+#define QG_MINBLOCKS 1
+#endif
+#ifndef QG_BLOCKSYNC
+#define QG_BLOCKSYNC 2
+#endif
 
 struct QgCounters {
     unsigned long long physics_steps, contacts, efc_rows, newton_iters, ls_evals, verts_tested, diverged,
@@ -119,15 +130,17 @@ DI double np_sum12(const double* v) {
 }
 
 template <bool DEBUG>
-__global__ void __launch_bounds__(QG_BLOCK)
-qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gverts, const int* __restrict__ vert_edge,
-               const int* __restrict__ mesh_edge, float4* __restrict__ S, int N, const float* __restrict__ action,
+__global__ void __launch_bounds__(QG_BLOCK, QG_MINBLOCKS)
+qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gverts, const int* __restrict__ vert_adj,
+               const int4* __restrict__ adj4, const int* __restrict__ vert_cadj, const int4* __restrict__ cadj4, float4* __restrict__ S, int N, const float* __restrict__ action,
                int clip_action, int frame_skip, float* __restrict__ obs, float* __restrict__ reward,
                float* __restrict__ terms, unsigned char* __restrict__ terminated, float* __restrict__ terminal_obs,
                QgStepOpts opts, QgCounters* __restrict__ ctr, QgDebugOut dbg) {
     extern __shared__ __align__(16) unsigned char smem[];
     QgModelC& P = *reinterpret_cast<QgModelC*>(smem);
     float4* sverts = reinterpret_cast<float4*>(smem + ((sizeof(QgModelC) + 15) & ~size_t(15)));
+    // per-warp scratch of the quad all-reduce, behind the vertex table
+    float* sred = reinterpret_cast<float*>(sverts + gm->nvert) + (threadIdx.x >> 5) * (QG_QR_SLOTS * 32);
     {
         const int4* src = reinterpret_cast<const int4*>(gm);
         int4* dst = reinterpret_cast<int4*>(smem);
@@ -137,11 +150,20 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
     }
     __syncthreads();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int env = t >> 2, leg = t & 3;
+    const int leg = t & 3;
+    // quads past the end of the batch shadow the last environment (same reads, no writes) so that every thread
+    // of the block reaches the same barriers
+    const bool valid = (t >> 2) < N;
+    const int env = valid ? (t >> 2) : N - 1;
+    if (!valid) { dbg.qacc = dbg.qacc_smooth = dbg.qfrc_bias = dbg.M = dbg.sensordata = nullptr; dbg.counts = nullptr; }
     const unsigned qm = 0xFu << (threadIdx.x & 28);
     unsigned long long cv[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    QuadRed qr;
+    qr.s = sred;
+    qr.lane = threadIdx.x & 31;
+    qr.qm = qm;
 
-    if (env < N) {
+    {
         LaneState L;
         int episode, flags;
         double first_cc;
@@ -162,13 +184,16 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
         const int max_iter = opts.max_iter, ls_iter = opts.ls_iter;
 #pragma unroll 1
         for (int s = 0; s < frame_skip; ++s) {
+#if QG_BLOCKSYNC
+            __syncthreads();
+#endif
             if (qsumi(lane_bad(L) ? 1 : 0, qm) > 0) {  // mj_checkPos / mj_checkVel
                 float c0 = L.ctrl[0], c1 = L.ctrl[1], c2 = L.ctrl[2];
                 reset_lane(P, L, leg, opts, env, episode);
                 L.ctrl[0] = c0; L.ctrl[1] = c1; L.ctrl[2] = c2;
                 diverged += (leg == 0);
             }
-            physics_step<DEBUG>(P, sverts, vert_edge, mesh_edge, L, leg, qm, max_iter, ls_iter, s == frame_skip - 1, so,
+            physics_step<DEBUG>(P, sverts, vert_adj, adj4, vert_cadj, cadj4, L, leg, qr, max_iter, ls_iter, s == frame_skip - 1, so,
                                 st, C, dbg, env);
         }
 
@@ -212,13 +237,13 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
                 }
                 double wv = opts.term_w[i] * v;
                 total += wv;
-                if (terms && leg == 0) terms[(size_t)env * opts.n_terms + i] = (float)wv;
+                if (terms && leg == 0 && valid) terms[(size_t)env * opts.n_terms + i] = (float)wv;
             }
         }
 
         // ---- termination (time limit is `terminated`, never truncated: quadruped.py:149-151,178-179)
         const bool term = (L.time >= opts.max_time) || (opts.flip_termination && so.zaxis.z < 0.f);
-        if (leg == 0) {
+        if (leg == 0 && valid) {
             reward[env] = (float)total;
             terminated[env] = term ? 1 : 0;
         }
@@ -233,6 +258,7 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
             else { o[30] = gate * so.vel.x; o[31] = gate * so.vel.y; o[32] = gate * so.vel.z; }
         };
         const bool do_reset = term && opts.auto_reset;
+        if (valid) {
         if (do_reset) {
             float z[3] = {0.f, 0.f, 0.f};
             (void)z;
@@ -256,15 +282,18 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
                 dbg.counts[env * 4 + 2] = st.niter; dbg.counts[env * 4 + 3] = st.nls;
             }
         }
+        }
         if (do_reset) {
             episode++;
             reset_lane(P, L, leg, opts, env, episode);
         }
-        store_lane(S, N, env, leg, L, episode, first_cc, flags);
+        if (valid) store_lane(S, N, env, leg, L, episode, first_cc, flags);
 
+        if (valid) {
         cv[0] = leg == 0 ? frame_skip : 0; cv[1] = st.ncon; cv[2] = st.nefc; cv[3] = st.niter;
         cv[4] = leg == 0 ? st.nls : 0; cv[5] = st.nvert; cv[6] = diverged; cv[7] = st.overflow;
         cv[8] = (leg == 0 && term) ? 1 : 0;
+        }
     }
 
     // ---- counters: warp shuffle reduce, one atomic per warp and counter

@@ -16,7 +16,7 @@
 #define QG_MAXVERT 1024     // unique hull vertices over all meshes (float4 each in shared memory)
 #define QG_MAX_TERMS_ 16
 #define QG_MAXMESH 8
-#define QG_DIRRES 4          // support-search start table: cube map, 6 faces x QG_DIRRES^2 cells per mesh
+#define QG_DIRRES 8          // support-search start table: cube map, 6 faces x QG_DIRRES^2 cells per mesh
 #define QG_DIRCELLS (6 * QG_DIRRES * QG_DIRRES)
 
 // state planes: float4 S[plane * N + env]
@@ -59,7 +59,8 @@ struct QgGeomC {
     float Rfac;     // 2 mu^2 (1+mu^2) * body_invweight0_trans  (pyramidal regulariser / ((1-imp)/imp))
     float tol2;     // (0.3 * rbound)^2 : minimum separation of extra plane-mesh contacts
     int vert0, nvert;  // slice of the vertex table
-    int edge0;         // offset of this mesh' edge lists in mesh_edge (global memory)
+    int edge0;         // start of this mesh's neighbour lists in the int4-packed adjacency table (int4 units)
+    int cedge0;        // same for the polytope-edge graph used by the hill climb
     int level;         // 0 = base, 1..3 = leg link
     int mesh;          // mesh id (row of dir_start)
 };

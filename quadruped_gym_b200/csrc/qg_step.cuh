@@ -69,7 +69,7 @@ __device__ __noinline__ float impedance(float r, float d0, float dmax, float wid
 //   Abb = Acommon (identical on the 4 lanes) + sum over lanes of Alocal,
 //   rb is identical on all lanes.
 DI void arrow_solve(const float* All, const float* Abl, const float* Alocal, const float* Acommon,
-                    const float* rb, const float* rl, unsigned qm, float* xb, float* xl) {
+                    const float* rb, const float* rl, const QuadRed& qr, float* xb, float* xl) {
     // LDL^T of the leg block
     float d0 = fmaxf(All[0], 1e-12f), i0 = 1.f / d0;
     float l10 = All[1] * i0, l20 = All[2] * i0;
@@ -95,12 +95,16 @@ DI void arrow_solve(const float* All, const float* Abl, const float* Alocal, con
 #pragma unroll
         for (int j = 0; j <= i; ++j) {
             float s = fmaf(Abl[i * 3], Y[j * 3], fmaf(Abl[i * 3 + 1], Y[j * 3 + 1], Abl[i * 3 + 2] * Y[j * 3 + 2]));
-            float loc = Alocal[IX6(i, j)] - s;
-            A[IX6(i, j)] = Acommon[IX6(i, j)] + qsum(loc, qm);
+            qr_put(qr, IX6(i, j), Alocal[IX6(i, j)] - s);
         }
-        float sb = fmaf(Abl[i * 3], t0, fmaf(Abl[i * 3 + 1], t1, Abl[i * 3 + 2] * t2));
-        b[i] = rb[i] - qsum(sb, qm);
+        qr_put(qr, 21 + i, fmaf(Abl[i * 3], t0, fmaf(Abl[i * 3 + 1], t1, Abl[i * 3 + 2] * t2)));
     }
+    qr_sync(qr);
+#pragma unroll
+    for (int i = 0; i < 21; ++i) A[i] = Acommon[i] + qr_get(qr, i);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) b[i] = rb[i] - qr_get(qr, 21 + i);
+    qr_sync(qr);
     // dense Cholesky of the 6x6 Schur complement (redundant on the 4 lanes, identical bits)
     float inv[6];
 #pragma unroll
@@ -145,7 +149,7 @@ DI void arrow_solve(const float* All, const float* Abl, const float* Alocal, con
 
 // y = M x on the arrow pattern
 DI void arrow_matvec(const float* Mll, const float* Mbl, const float* Mbb, const float* xb, const float* xl,
-                     unsigned qm, float* yb, float* yl) {
+                     const QuadRed& qr, float* yb, float* yl) {
     yl[0] = fmaf(Mll[0], xl[0], fmaf(Mll[1], xl[1], Mll[2] * xl[2]));
     yl[1] = fmaf(Mll[1], xl[0], fmaf(Mll[3], xl[1], Mll[4] * xl[2]));
     yl[2] = fmaf(Mll[2], xl[0], fmaf(Mll[4], xl[1], Mll[5] * xl[2]));
@@ -156,13 +160,16 @@ DI void arrow_matvec(const float* Mll, const float* Mbl, const float* Mbb, const
         yl[2] = fmaf(Mbl[r * 3 + 2], xb[r], yl[2]);
     }
 #pragma unroll
+    for (int r = 0; r < 6; ++r) qr_put(qr, r, fmaf(Mbl[r * 3], xl[0], fmaf(Mbl[r * 3 + 1], xl[1], Mbl[r * 3 + 2] * xl[2])));
+    qr_sync(qr);
+#pragma unroll
     for (int r = 0; r < 6; ++r) {
-        float s = fmaf(Mbl[r * 3], xl[0], fmaf(Mbl[r * 3 + 1], xl[1], Mbl[r * 3 + 2] * xl[2]));
         float t = 0.f;
 #pragma unroll
         for (int k = 0; k < 6; ++k) t = fmaf(Mbb[r >= k ? IX6(r, k) : IX6(k, r)], xb[k], t);
-        yb[r] = t + qsum(s, qm);
+        yb[r] = t + qr_get(qr, r);
     }
+    qr_sync(qr);
 }
 
 // spatial velocity prefixes of a generalised vector: U[k] + W[k] x p = velocity of a point p on link k
@@ -191,32 +198,53 @@ __device__ __noinline__ float2 sincos_ni(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// plane-vs-hull collision of all geoms this lane owns (mjc_PlaneConvex restated): oriented-box cull,
-// hill-climbing support search on the hull graph (exact for a convex hull), then up to 3 hull-graph
-// neighbours of the support vertex.  `fr` holds the lane's 4 link frames (level 0 = base): 9 rotation
-// entries (row major, link -> B) and 3 position entries each.
-DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const int* __restrict__ vert_edge,
-                     const int* __restrict__ mesh_edge, int leg, const float* fr, v3 up, float zb, Contacts& C,
+// plane-vs-hull collision of all geoms this lane owns (mjc_PlaneConvex restated).
+//   pass 1: oriented-box cull of every geom (20 flops each) -> bit mask of candidates;
+//   pass 2: per candidate, hill-climbing support search on the hull graph (exact for a convex hull; start
+//           vertex from a cube-map table of the search direction; neighbour lists are padded to int4
+//           groups so that four neighbours are fetched and evaluated per step), then up to 3 hull-graph
+//           neighbours of the support vertex become extra contacts.
+// Lanes walk their own candidate lists in lockstep, so the j-th candidates of all lanes overlap.
+// `fr` holds the lane's 4 link frames (level 0 = base): rotation (row major, link -> B) and position.
+DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const int* __restrict__ vert_adj,
+                     const int4* __restrict__ adj4, const int* __restrict__ vert_cadj,
+                     const int4* __restrict__ cadj4, int leg, const float* fr, v3 up, float zb, Contacts& C,
                      StepStats& st) {
     const int ng = P.ngeom[leg];
+    v3 dB[4];      // "up" in each link frame
+    float hk[4];   // height of each link origin above the plane
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        m3 Rk = ldm3(fr + 12 * k);
+        dB[k] = tmul(Rk, up);
+        hk[k] = zb + dot(up, ld3(fr + 12 * k + 9));
+    }
+    unsigned cand = 0;
 #pragma unroll 1
     for (int g = 0; g < ng; ++g) {
         const QgGeomC& G = P.geom[leg][g];
-        const float* f = fr + 12 * G.level;
-        m3 Rk = ldm3(f);
-        v3 pk = ld3(f + 9);
-        v3 ctr = pk + mul(Rk, ld3(G.pos));
-        float zc = zb + dot(up, ctr);
-        m3 RB = matmul(Rk, ldm3(G.R));  // mesh frame -> B
-        v3 dl = tmul(RB, up);           // "up" in the mesh frame
+        const int lev = G.level;
+        v3 d = sel4(dB, lev);
+        float zc = (lev == 0 ? hk[0] : (lev == 1 ? hk[1] : (lev == 2 ? hk[2] : hk[3]))) + dot(d, ld3(G.pos));
+        v3 dl = tmul(ldm3(G.R), d);  // "up" in the mesh frame
         float ext = fmaf(fabsf(dl.x), G.half[0], fmaf(fabsf(dl.y), G.half[1], fabsf(dl.z) * G.half[2]));
-        float margin = G.margin;
-        if (zc - ext > margin) continue;  // oriented-box cull (conservative; same contacts as any cull)
+        if (zc - ext <= G.margin) cand |= 1u << g;  // oriented-box cull (conservative; same contacts as any cull)
+    }
+#pragma unroll 1
+    while (cand) {
+        const int g = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const QgGeomC& G = P.geom[leg][g];
+        const int lev = G.level;
+        const float margin = G.margin;
+        v3 d = sel4(dB, lev);
+        float zc = (lev == 0 ? hk[0] : (lev == 1 ? hk[1] : (lev == 2 ? hk[2] : hk[3]))) + dot(d, ld3(G.pos));
+        v3 dl = tmul(ldm3(G.R), d);
         const float4* __restrict__ vt = verts + G.vert0;
-        const int* __restrict__ ve = vert_edge + G.vert0;
-        const int* __restrict__ el = mesh_edge + G.edge0;
-        // support vertex along -up: start from the cube-map cell of the direction, then hill-climb on the
-        // hull graph (a vertex of a convex polytope that is not the minimiser has a strictly lower neighbour)
+        const int* __restrict__ va = vert_adj + G.vert0;
+        const int4* __restrict__ el = adj4 + G.edge0;
+        const int* __restrict__ vc = vert_cadj + G.vert0;
+        const int4* __restrict__ cl = cadj4 + G.cedge0;
         int best;
         {
             float ax = fabsf(dl.x), ay = fabsf(dl.y), az = fabsf(dl.z);
@@ -237,17 +265,23 @@ DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const 
         int nev = 1;
 #pragma unroll 1
         for (;;) {
-            const int* __restrict__ e = el + __ldg(ve + best);
+            const int4* __restrict__ e = cl + __ldg(vc + best);
             int nxt = -1;
             float hn = hbest;
 #pragma unroll 1
             for (;;) {
-                int nb = __ldg(e++);
-                if (nb < 0) break;
-                float4 v = vt[nb];
-                float hh = fmaf(dl.x, v.x, fmaf(dl.y, v.y, dl.z * v.z));
-                nev++;
-                if (hh < hn) { hn = hh; nxt = nb; }
+                int4 nb = __ldg(e++);
+                float4 v0 = vt[max(nb.x, 0)], v1 = vt[max(nb.y, 0)], v2 = vt[max(nb.z, 0)], v3_ = vt[max(nb.w, 0)];
+                float h0 = fmaf(dl.x, v0.x, fmaf(dl.y, v0.y, dl.z * v0.z));
+                float h1 = fmaf(dl.x, v1.x, fmaf(dl.y, v1.y, dl.z * v1.z));
+                float h2 = fmaf(dl.x, v2.x, fmaf(dl.y, v2.y, dl.z * v2.z));
+                float h3 = fmaf(dl.x, v3_.x, fmaf(dl.y, v3_.y, dl.z * v3_.z));
+                if (nb.x >= 0 && h0 < hn) { hn = h0; nxt = nb.x; }
+                if (nb.y >= 0 && h1 < hn) { hn = h1; nxt = nb.y; }
+                if (nb.z >= 0 && h2 < hn) { hn = h2; nxt = nb.z; }
+                if (nb.w >= 0 && h3 < hn) { hn = h3; nxt = nb.w; }
+                nev += (nb.x >= 0) + (nb.y >= 0) + (nb.z >= 0) + (nb.w >= 0);
+                if (nb.w < 0) break;
             }
             if (nxt < 0) break;
             best = nxt;
@@ -255,13 +289,16 @@ DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const 
         }
         st.nvert += nev;
         if (zc + hbest > margin) continue;
-        // support vertex first, then its hull-graph neighbours (up to 4 contacts per geom)
-        const int* __restrict__ e = el + __ldg(ve + best);
-        int cnt = 0, cand = best;
+        // support vertex first, then its hull-graph neighbours in list order (up to 4 contacts per geom)
+        m3 Rk = ldm3(fr + 12 * lev);
+        v3 ctr = ld3(fr + 12 * lev + 9) + mul(Rk, ld3(G.pos));
+        m3 RB = matmul(Rk, ldm3(G.R));  // mesh frame -> B
+        const int* __restrict__ e = reinterpret_cast<const int*>(el + __ldg(va + best));
+        int cnt = 0, cand_v = best;
         v3 prev0 = V3(0, 0, 0), prev1 = prev0, prev2 = prev0;
 #pragma unroll 1
         for (;;) {
-            float4 v = vt[cand];
+            float4 v = vt[cand_v];
             v3 xv = ctr + mul(RB, V3(v.x, v.y, v.z));
             float dv = zb + dot(up, xv);
             bool ok = (cnt == 0) || (dv <= margin);
@@ -287,22 +324,23 @@ DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const 
                         C.mu[c] = G.mu;
                         C.Bd[c] = G.B;
                         C.Kr[c] = G.K * imp * r;
-                        C.lev[c] = G.level;
+                        C.lev[c] = lev;
                     } else st.overflow++;
                 }
             }
             if (cnt >= 4) break;
             int nb = __ldg(e++);
             if (nb < 0) break;
-            cand = nb;
+            cand_v = nb;
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 template <bool DEBUG>
-DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const int* __restrict__ vert_edge,
-                     const int* __restrict__ mesh_edge, LaneState& S, int leg, unsigned qm,
+DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const int* __restrict__ vert_adj,
+                     const int4* __restrict__ adj4, const int* __restrict__ vert_cadj,
+                     const int4* __restrict__ cadj4, LaneState& S, int leg, const QuadRed& qr,
                      int max_iter, int ls_iter, bool want_sensors, SensorOut& so, StepStats& st, Contacts& C,
                      const QgDebugOut& dbg, int env) {
     const float h = P.timestep;
@@ -342,7 +380,10 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
         }
     }
     C.n = 0;
-    collide_lane(P, verts, vert_edge, mesh_edge, leg, fr, up, zb, C, st);
+    collide_lane(P, verts, vert_adj, adj4, vert_cadj, cadj4, leg, fr, up, zb, C, st);
+#if QG_BLOCKSYNC >= 2
+    __syncthreads();  // collision time varies per warp: re-align before the straight-line dynamics code
+#endif
 
     // ---- velocity recursion and inertias along the chain
     v3 sl[3], sa[3];        // joint spatial motion about the B origin: linear p x a, angular a
@@ -424,18 +465,25 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
         I0.xx = P.base_I[0]; I0.yy = P.base_I[1]; I0.zz = P.base_I[2];
         I0.xy = P.base_I[3]; I0.xz = P.base_I[4]; I0.yz = P.base_I[5];
         v3 N0 = cross(S.om, mul(I0, S.om)) + cross(c0, F0);
-        fsum = qsum(fsum, qm) + F0;
-        nsum = qsum(nsum, qm) + N0;
-        float mt = qsum(cm, qm) + m0;
-        v3 ht = qsum(chv, qm) + m0 * c0;
+        qr_put(qr, 0, fsum.x); qr_put(qr, 1, fsum.y); qr_put(qr, 2, fsum.z);
+        qr_put(qr, 3, nsum.x); qr_put(qr, 4, nsum.y); qr_put(qr, 5, nsum.z);
+        qr_put(qr, 6, cm); qr_put(qr, 7, chv.x); qr_put(qr, 8, chv.y); qr_put(qr, 9, chv.z);
+        qr_put(qr, 10, cI.xx); qr_put(qr, 11, cI.yy); qr_put(qr, 12, cI.zz);
+        qr_put(qr, 13, cI.xy); qr_put(qr, 14, cI.xz); qr_put(qr, 15, cI.yz);
+        qr_sync(qr);
+        fsum = V3(qr_get(qr, 0), qr_get(qr, 1), qr_get(qr, 2)) + F0;
+        nsum = V3(qr_get(qr, 3), qr_get(qr, 4), qr_get(qr, 5)) + N0;
+        float mt = qr_get(qr, 6) + m0;
+        v3 ht = V3(qr_get(qr, 7), qr_get(qr, 8), qr_get(qr, 9)) + m0 * c0;
         float c2 = dot(c0, c0);
         s3 It;
-        It.xx = qsum(cI.xx, qm) + I0.xx + m0 * (c2 - c0.x * c0.x);
-        It.yy = qsum(cI.yy, qm) + I0.yy + m0 * (c2 - c0.y * c0.y);
-        It.zz = qsum(cI.zz, qm) + I0.zz + m0 * (c2 - c0.z * c0.z);
-        It.xy = qsum(cI.xy, qm) + I0.xy - m0 * c0.x * c0.y;
-        It.xz = qsum(cI.xz, qm) + I0.xz - m0 * c0.x * c0.z;
-        It.yz = qsum(cI.yz, qm) + I0.yz - m0 * c0.y * c0.z;
+        It.xx = qr_get(qr, 10) + I0.xx + m0 * (c2 - c0.x * c0.x);
+        It.yy = qr_get(qr, 11) + I0.yy + m0 * (c2 - c0.y * c0.y);
+        It.zz = qr_get(qr, 12) + I0.zz + m0 * (c2 - c0.z * c0.z);
+        It.xy = qr_get(qr, 13) + I0.xy - m0 * c0.x * c0.y;
+        It.xz = qr_get(qr, 14) + I0.xz - m0 * c0.x * c0.z;
+        It.yz = qr_get(qr, 15) + I0.yz - m0 * c0.y * c0.z;
+        qr_sync(qr);
 #pragma unroll
         for (int i = 0; i < 21; ++i) Mbb[i] = 0.f;
         Mbb[IX6(0, 0)] = mt + P.base_arm[0]; Mbb[IX6(1, 1)] = mt + P.base_arm[1]; Mbb[IX6(2, 2)] = mt + P.base_arm[2];
@@ -510,7 +558,10 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
 #pragma unroll
         for (int k = 0; k < 4; ++k) C.jar[k][c] = fmaf(C.Bd[c], rv[k], C.Kr[c]);  // = -aref_k
     }
-    const int nefc = qsumi(4 * nc + nlim, qm);
+    qr_put(qr, 0, (float)(4 * nc + nlim));
+    qr_sync(qr);
+    const int nefc = (int)qr_get(qr, 0);
+    qr_sync(qr);
     st.ncon += nc;
     st.nefc += 4 * nc + nlim;
 
@@ -530,10 +581,26 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
     for (int i = 0; i < 3; ++i) { rl[i] = fsl[i]; fcl[i] = 0.f; }
     int phase = 0, iter = 0;
     float cost_old = 0.f;
+    bool done = false;
 #pragma unroll 1
     for (;;) {
-        arrow_solve(Hll, Hbl, Hc, Mbb, rb, rl, qm, xb, xl);
-        if (phase == 2) break;
+#if QG_BLOCKSYNC
+        // block-uniform trip count: the warps of a block walk the solver code together, so that one
+        // instruction-cache fill serves all of them (instruction fetch is the limiter of this kernel)
+        if (!__syncthreads_or(!done)) break;
+#if QG_BLOCKSYNC >= 3
+        if (!done) arrow_solve(Hll, Hbl, Hc, Mbb, rb, rl, qr, xb, xl);
+        __syncthreads();
+        if (done) continue;
+#else
+        if (done) continue;
+        arrow_solve(Hll, Hbl, Hc, Mbb, rb, rl, qr, xb, xl);
+#endif
+#else
+        if (done) break;
+        arrow_solve(Hll, Hbl, Hc, Mbb, rb, rl, qr, xb, xl);
+#endif
+        if (phase == 2) { done = true; continue; }
         bool conv = false;
         if (phase == 0) {
 #pragma unroll
@@ -576,13 +643,16 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                     cs += (lsgn[k] != 0.f && js < 0.f) ? 0.5f * lD[k] * js * js : 0.f;
                 }
                 float Mwb[6], Mwl[3];
-                arrow_matvec(Mll, Mbl, Mbb, wb, S.wj, qm, Mwb, Mwl);
+                arrow_matvec(Mll, Mbl, Mbb, wb, S.wj, qr, Mwb, Mwl);
                 float gl = 0.f, gb = 0.f;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) gl += 0.5f * (Mwl[k] - fsl[k]) * (S.wj[k] - a0l[k]);
 #pragma unroll
                 for (int r = 0; r < 6; ++r) gb += 0.5f * (Mwb[r] - fsb[r]) * (wb[r] - a0b[r]);
-                float cost_w = qsum(cw + gl, qm) + gb, cost_s = qsum(cs, qm);
+                qr_put(qr, 0, cw + gl); qr_put(qr, 1, cs);
+                qr_sync(qr);
+                float cost_w = qr_get(qr, 0) + gb, cost_s = qr_get(qr, 1);
+                qr_sync(qr);
                 if (cost_w < cost_s) {
 #pragma unroll
                     for (int i = 0; i < 6; ++i) { ab[i] = wb[i]; Mab[i] = Mwb[i]; }
@@ -600,7 +670,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
         } else {
             // ---- (xb, xl) is the Newton direction: exact line search on the convex piecewise quadratic
             float Mvb[6], Mvl[3];
-            arrow_matvec(Mll, Mbl, Mbb, xb, xl, qm, Mvb, Mvl);
+            arrow_matvec(Mll, Mbl, Mbb, xb, xl, qr, Mvb, Mvl);
             float q1l = 0.f, q2l = 0.f, q1b = 0.f, q2b = 0.f;
 #pragma unroll
             for (int k = 0; k < 3; ++k) { q1l += xl[k] * (Mal[k] - fsl[k]); q2l += 0.5f * xl[k] * Mvl[k]; }
@@ -635,13 +705,18 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                     flips += ((j0 < 0.f) != (j1 < 0.f)) ? 1 : 0;
                 }
             }
-            const float q1 = qsum(q1l, qm) + q1b, q2 = qsum(q2l, qm) + q2b;
-            flips = qsumi(flips, qm);
+            qr_put(qr, 0, q1l); qr_put(qr, 1, q2l); qr_put(qr, 2, (float)flips);
+            qr_put(qr, 3, z1); qr_put(qr, 4, e1); qr_put(qr, 5, e2);
+            qr_sync(qr);
+            const float q1 = qr_get(qr, 0) + q1b, q2 = qr_get(qr, 1) + q2b;
+            flips = (int)qr_get(qr, 2);
+            const float z1s = qr_get(qr, 3), e1s = qr_get(qr, 4), e2s = qr_get(qr, 5);
+            qr_sync(qr);
             st.nls++;
             float alpha = 1.f;
             if (flips != 0) {
-                float d10 = qsum(z1, qm) + q1;                         // derivative at 0 (< 0: descent direction)
-                float d1 = qsum(e1, qm) + q1 + 2.f * q2, d2 = qsum(e2, qm) + 2.f * q2;
+                float d10 = z1s + q1;                                  // derivative at 0 (< 0: descent direction)
+                float d1 = e1s + q1 + 2.f * q2, d2 = e2s + 2.f * q2;
                 float gtol = 1e-4f * fabsf(d10);
                 float lo = 0.f, hi = -1.f;
                 if (d10 >= 0.f) alpha = 0.f;
@@ -668,8 +743,11 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                             float xx = fmaf(alpha, ljv[k], ljar[k]);
                             if (lsgn[k] != 0.f && xx < 0.f) { e1 = fmaf(lD[k] * ljv[k], xx, e1); e2 = fmaf(lD[k] * ljv[k], ljv[k], e2); }
                         }
-                        d1 = qsum(e1, qm) + q1 + 2.f * alpha * q2;
-                        d2 = qsum(e2, qm) + 2.f * q2;
+                        qr_put(qr, 0, e1); qr_put(qr, 1, e2);
+                        qr_sync(qr);
+                        d1 = qr_get(qr, 0) + q1 + 2.f * alpha * q2;
+                        d2 = qr_get(qr, 1) + 2.f * q2;
+                        qr_sync(qr);
                         st.nls++;
                     }
                 }
@@ -724,17 +802,23 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
             for (int k = 0; k < 3; ++k) gauss_l += 0.5f * (Mal[k] - fsl[k]) * (al[k] - a0l[k]);
 #pragma unroll
             for (int r = 0; r < 6; ++r) gauss_b += 0.5f * (Mab[r] - fsb[r]) * (ab[r] - a0b[r]);
-            cost = qsum(cost + gauss_l, qm) + gauss_b;
-            Fb = qsum(Fb, qm);
-            Nb = qsum(Nb, qm);
-            fcb[0] = Fb.x; fcb[1] = Fb.y; fcb[2] = Fb.z; fcb[3] = Nb.x; fcb[4] = Nb.y; fcb[5] = Nb.z;
+            qr_put(qr, 0, cost + gauss_l);
+            qr_put(qr, 1, Fb.x); qr_put(qr, 2, Fb.y); qr_put(qr, 3, Fb.z);
+            qr_put(qr, 4, Nb.x); qr_put(qr, 5, Nb.y); qr_put(qr, 6, Nb.z);
             float g2 = 0.f, g2b = 0.f;
 #pragma unroll
             for (int k = 0; k < 3; ++k) { fcl[k] = tau[k]; gl[k] = Mal[k] - fsl[k] - tau[k]; g2 += gl[k] * gl[k]; }
+            qr_put(qr, 7, g2);
+            qr_sync(qr);
+            cost = qr_get(qr, 0) + gauss_b;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) fcb[r] = qr_get(qr, 1 + r);
+            g2 = qr_get(qr, 7);
+            qr_sync(qr);
 #pragma unroll
             for (int r = 0; r < 6; ++r) { gb[r] = Mab[r] - fsb[r] - fcb[r]; g2b += gb[r] * gb[r]; }
             if (phase == 1 && !conv) {
-                float gradient = P.scale * sqrtf(qsum(g2, qm) + g2b);
+                float gradient = P.scale * sqrtf(g2 + g2b);
                 float improvement = P.scale * (cost_old - cost);
                 conv = improvement < P.tol || gradient < P.tol || iter >= max_iter;
             }

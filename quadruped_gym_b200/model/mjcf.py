@@ -109,6 +109,8 @@ class Mesh:
     hull_vert: np.ndarray = None  # hull vertices in the re-centred, re-oriented mesh frame [h,3]
     hull_edgeadr: np.ndarray = None  # [h] start of each vertex' neighbour list in hull_edge
     hull_edge: np.ndarray = None  # neighbour lists, each terminated by -1
+    hull_cedgeadr: np.ndarray = None  # same layout, polytope edges only (no diagonals of coplanar facets):
+    hull_cedge: np.ndarray = None     # the graph the kernels hill-climb on for the support search
     aabb_absmax: np.ndarray = None  # per-axis max |coord| in the mesh frame
 
 
@@ -185,6 +187,23 @@ def _hull(vert):
                 lw = local[int(w)]
                 if lw != lu and lw not in nbr[lu]:
                     nbr[lu].append(lw)
+    # polytope edges only: drop the diagonals qhull's triangulation (Qt) puts inside merged coplanar facets.
+    # A linear function over a convex polytope still has a strictly improving polytope-edge neighbour at every
+    # non-optimal vertex, and the fan centres of flat faces lose their ~100 spokes.
+    edge_faces = {}
+    for fi, tri in enumerate(h.simplices):
+        for a, b in ((0, 1), (1, 2), (0, 2)):
+            key = (min(int(tri[a]), int(tri[b])), max(int(tri[a]), int(tri[b])))
+            edge_faces.setdefault(key, []).append(fi)
+    cnbr: List[List[int]] = [[] for _ in ids]
+    for lu, lst in enumerate(nbr):
+        gu = int(ids[lu])
+        for lw in lst:
+            gw = int(ids[lw])
+            fs = edge_faces[(min(gu, gw), max(gu, gw))]
+            diagonal = len(fs) == 2 and np.allclose(h.equations[fs[0]], h.equations[fs[1]], rtol=0, atol=1e-10)
+            if not diagonal:
+                cnbr[lu].append(lw)
     # orient hull faces outward for the "convex" inertia mode
     tris = h.simplices.copy()
     cen = vert[ids].mean(0)
@@ -192,13 +211,13 @@ def _hull(vert):
         a, b, c = vert[tri]
         if np.dot(np.cross(b - a, c - a), a - cen) < 0:
             tris[k] = tri[[0, 2, 1]]
-    return ids, nbr, tris
+    return ids, nbr, tris, cnbr
 
 
 def process_mesh(name: str, path: str, mode: str = "legacy") -> Mesh:
     vert, face = load_obj(path)
     m = Mesh(name=name, vert=vert, face=face)
-    ids, nbr, hull_tris = _hull(vert)
+    ids, nbr, hull_tris, cnbr = _hull(vert)
     if mode == "convex":
         volume, com, inertia = _mesh_mass_props(vert, hull_tris, "exact")
     else:
@@ -221,6 +240,13 @@ def process_mesh(name: str, path: str, mode: str = "legacy") -> Mesh:
         edges.append(-1)
     m.hull_edgeadr = np.array(adr, dtype=np.int32)
     m.hull_edge = np.array(edges, dtype=np.int32)
+    adr, edges = [], []
+    for lst in cnbr:
+        adr.append(len(edges))
+        edges.extend(lst)
+        edges.append(-1)
+    m.hull_cedgeadr = np.array(adr, dtype=np.int32)
+    m.hull_cedge = np.array(edges, dtype=np.int32)
     m.aabb_absmax = np.abs(local).max(0)
     return m
 
@@ -599,6 +625,7 @@ def compile_mjcf(path: str, mesh_inertia: str = "legacy") -> CompiledModel:
     A["geom_solref"] = np.array(g_solref)
     A["geom_solimp"] = np.array(g_solimp)
     vadr, vnum, eadr, verts, vedge, edges = [], [], [], [], [], []
+    ceadr, cvedge, cedges = [], [], []
     for name in mesh_names:
         me = meshes[name]
         vadr.append(sum(vnum))
@@ -607,12 +634,19 @@ def compile_mjcf(path: str, mesh_inertia: str = "legacy") -> CompiledModel:
         verts.append(me.hull_vert)
         vedge.append(me.hull_edgeadr)
         edges.extend(me.hull_edge.tolist())
+        ceadr.append(len(cedges))
+        cvedge.append(me.hull_cedgeadr)
+        cedges.extend(me.hull_cedge.tolist())
     A["mesh_vertadr"] = np.array(vadr, dtype=np.int32)
     A["mesh_vertnum"] = np.array(vnum, dtype=np.int32)
     A["mesh_edgeadr"] = np.array(eadr, dtype=np.int32)  # start of the mesh' edge list in mesh_edge
     A["mesh_vert"] = np.concatenate(verts, 0)
     A["mesh_vert_edge"] = np.concatenate(vedge, 0).astype(np.int32)  # per vertex, relative to mesh_edgeadr
     A["mesh_edge"] = np.array(edges, dtype=np.int32)  # local vertex ids, -1 terminates a list
+    # polytope-edge graph (support-search hill climbing); same layout as the three sections above
+    A["mesh_cedgeadr"] = np.array(ceadr, dtype=np.int32)
+    A["mesh_vert_cedge"] = np.concatenate(cvedge, 0).astype(np.int32)
+    A["mesh_cedge"] = np.array(cedges, dtype=np.int32)
 
     cm = CompiledModel(arrays=A, sensor_names=sensor_names, sensor_adr=sensor_adr, sensor_dim=sensor_dim,
                        joint_names=joint_names, body_names=[b["name"] for b in bodies], source=path)
