@@ -253,6 +253,12 @@ def run_ours(a):
         if not a.profile:
             _lib.lib().qg_fp32_peak(local, 4096, ctypes.byref(tf))
         launch_ms = float(np.mean(step_ms))
+        traffic = None   # dram bytes per launch from the committed ncu capture, scaled to this batch size
+        try:
+            pm = json.load(open(os.path.join(ROOT, "profiles", "r1_step_kernel_metrics.json")))
+            traffic = (pm["dram__bytes_read.sum"] + pm["dram__bytes_write.sum"]) / pm["envs"] * envs
+        except Exception:
+            pass
         algo_bytes = 737.0 * envs  # 737 B per env.step() per env
         hbm_ach = algo_bytes / (launch_ms * 1e-3) / 1e9
         fp32_ach = fl * envs * fs / (launch_ms * 1e-3) / 1e12
@@ -270,7 +276,7 @@ def run_ours(a):
                     "d2h_bytes_per_step": envs * (33 * 4 + 4 + 1)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "peak_source": peak_src,
                          "note": "kernel is FP32-issue bound by design (SURVEY 8d); see roofline_fp32"},
             "roofline_fp32": {"bound": "fp32-cuda-core", "achieved": fp32_ach, "peak": tf.value, "unit": "TFLOP/s",
                               "frac": fp32_ach / tf.value if tf.value else None, "flops_per_physics_step": fl,

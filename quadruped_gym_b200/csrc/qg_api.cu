@@ -49,6 +49,7 @@ struct qg_batch {
     QgCounters* d_ctr;
     QgStepOpts opts;
     size_t smem;
+    int num_sms;
     // pinned + device staging for the host-buffer path
     float *h_act, *h_obs, *h_rew, *d_act, *d_obs, *d_rew;
     unsigned char *h_term, *d_term;
@@ -455,6 +456,11 @@ extern "C" int qg_batch_create(const qg_model* m, int n_envs, int device, qg_bat
     b->n = n_envs;
     b->device = device;
     default_opts(m, b->opts);
+    {
+        cudaDeviceProp prop;
+        CUDA_OK(cudaGetDeviceProperties(&prop, device));
+        b->num_sms = prop.multiProcessorCount;
+    }
     size_t nv = m->verts.size() / 4;
     CUDA_OK(cudaMalloc(&b->d_model, sizeof(QgModelC)));
     CUDA_OK(cudaMalloc(&b->d_verts, sizeof(float4) * (nv ? nv : 1)));
@@ -524,6 +530,13 @@ extern "C" int qg_set_reward_table(qg_batch* b, int n_terms, const int* term_ids
 
 static inline int nblocks(int n_envs) { return (4 * n_envs + QG_BLOCK - 1) / QG_BLOCK; }
 
+// step-kernel block size: QG_BLOCK for large batches, smaller blocks when the grid would not fill the SMs twice
+static int step_block(const qg_batch* b) {
+    int blk = QG_BLOCK;
+    while (blk > 64 && (4 * b->n + blk - 1) / blk < 2 * b->num_sms) blk >>= 1;
+    return blk;
+}
+
 extern "C" int qg_reset(qg_batch* b, const uint8_t* mask_dev, uint64_t seed, int random_yaw, long long env_offset,
                         void* stream) {
     if (!b) return fail(QG_EINVAL, "batch is NULL");
@@ -541,7 +554,8 @@ extern "C" int qg_reset(qg_batch* b, const uint8_t* mask_dev, uint64_t seed, int
 template <bool DEBUG>
 static int launch_step(qg_batch* b, const float* action, int clip, int frame_skip, float* obs, float* reward, float* terms,
                        unsigned char* terminated, float* terminal_obs, QgDebugOut dbg, cudaStream_t st) {
-    qg_step_kernel<DEBUG><<<nblocks(b->n), QG_BLOCK, b->smem, st>>>(b->d_model, b->d_verts, b->d_vert_adj, b->d_adj4, b->d_vert_cadj, b->d_cadj4,
+    const int blk = step_block(b);
+    qg_step_kernel<DEBUG><<<(4 * b->n + blk - 1) / blk, blk, b->smem, st>>>(b->d_model, b->d_verts, b->d_vert_adj, b->d_adj4, b->d_vert_cadj, b->d_cadj4,
                                                                      b->d_state, b->n, action, clip, frame_skip, obs, reward,
                                                                      terms, terminated, terminal_obs, b->opts, b->d_ctr, dbg);
     g_launches++;

@@ -47,7 +47,7 @@ def _mark(txt):
 
 _M = [("base frame + FK", "DI void physics_step("), ("collision", "collide_lane(P, verts"), ("dynamics (RNE+CRB+act)", "// ---- velocity recursion and inertias"),
       ("rows setup", "// ---- constraint rows: joint limits"), ("phase: init", "// ---- phase machine around ONE arrow solve"),
-      ("phase: arrow_solve", "arrow_solve(Hll, Hbl, Hc, Mbb"), ("phase: warmstart", "if (phase == 2) break;"),
+      ("phase: arrow_solve", "arrow_solve(Hll, Hbl, Hc, Mbb"), ("phase: warmstart", "if (phase == 2) { done = true; continue; }"),
       ("phase: linesearch", "is the Newton direction: exact line search"), ("phase: update", "float gb[6], gl[3];"),
       ("phase: implicit prep", "// ---- next solve: implicit integration"), ("phase: hessian", "// ---- next solve: Newton direction"),
       ("sensors+integrate", "// ---- sensors of this forward pass")]
