@@ -530,10 +530,11 @@ extern "C" int qg_set_reward_table(qg_batch* b, int n_terms, const int* term_ids
 
 static inline int nblocks(int n_envs) { return (4 * n_envs + QG_BLOCK - 1) / QG_BLOCK; }
 
-// step-kernel block size: QG_BLOCK for large batches, smaller blocks when the grid would not fill the SMs twice
+// step-kernel block size: QG_BLOCK (warps of a block share instruction-cache fills through the block barriers);
+// one halving for small batches whose grid would leave SMs without a block
 static int step_block(const qg_batch* b) {
     int blk = QG_BLOCK;
-    while (blk > 64 && (4 * b->n + blk - 1) / blk < 2 * b->num_sms) blk >>= 1;
+    if (blk > 128 && (4 * b->n + blk - 1) / blk < b->num_sms) blk >>= 1;
     return blk;
 }
 
