@@ -147,6 +147,34 @@ int qg_debug_step(qg_batch* b, const float* ctrl_dev, float* qacc_dev, float* qa
 
 int qg_get_counters(qg_batch* b, qg_counters* out_host, int reset, void* stream);
 
+/* --- WalkingQuadrupedEnv reward stack (src/envs/walking_quad.py:9-428) -------------------------------------
+ * qg_walk_enable allocates the per-env walking state: command inputs (control_inputs.py:9-12), ideal position
+ * (walking_quad.py:88-94), control-cost memory (:255-270), derivative memory (:388-396) and the online
+ * frequency / amplitude estimator (math_utils.py:11-133; `window` = ceil(2/(min_freq*dt)) samples x 12 channels).
+ * dt = timestep*frame_skip as ONE float64 product (how the reference computes it); settling_time masks actions to
+ * the joint centres while data.time < settling_time (walking_quad.py:142-143).  sample_opts = {min_speed,
+ * max_speed, fixed_heading_angle, fixed_velocity_angle, fixed_speed}, sample_has = which of the three fixed_*
+ * are given (control_inputs.py:88-116); random_controls resamples the command at every reset (:121-122). */
+#define QG_WALK_NTERMS 11   /* WalkingQuadrupedEnv.reward_keys, walking_quad.py:331-350 */
+int qg_walk_enable(qg_batch* b, int window, double dt, double timestep, int frame_skip, double settling_time,
+                   int random_controls, const double* sample_opts, const int* sample_has);
+/* reset() bookkeeping of WalkingQuadrupedEnv (walking_quad.py:96-126); hard != 0 also clears the state that
+ * survives reset() in the reference (estimator, first control cost) and re-keys the command sampler. */
+int qg_walk_reset(qg_batch* b, const uint8_t* mask_dev, int hard, uint64_t seed, long long env_offset, void* stream);
+/* set_velocity_speed_alpha + set_orientation (control_inputs.py:36-51): [N,3] = speed, alpha, theta (float64) */
+int qg_walk_set_commands(qg_batch* b, const double* speed_alpha_theta_dev, const uint8_t* mask_dev, void* stream);
+/* any pointer may be NULL: velocity/heading/global_velocity/ideal_position [N,3], f_est/a_est [12,N] (float64) */
+int qg_walk_get_commands(qg_batch* b, double* velocity_dev, double* heading_dev, double* global_velocity_dev,
+                         double* ideal_position_dev, double* f_est_dev, double* a_est_dev, void* stream);
+/* One WalkingQuadrupedEnv.step() of bookkeeping after the physics launch (run qg_step with auto_reset = 0):
+ * ideal position, estimator.update(previous ctrl), the 11 reward terms and their sum (float64 arithmetic;
+ * float32 and/or float64 outputs), then for terminated envs the walking reset() bookkeeping, the zero reset
+ * observation and the terminal observation.  ctrl_dev NULL = the batch's data.ctrl.  The caller then resets the
+ * physics of the terminated envs with qg_reset(mask = terminated_dev). */
+int qg_walk_step(qg_batch* b, float* obs_dev, const float* ctrl_dev, const uint8_t* terminated_dev,
+                 float* terminal_obs_dev, float* reward_dev, float* terms_dev, double* reward64_dev,
+                 double* terms64_dev, int auto_reset, void* stream);
+
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 unsigned long long qg_launch_count(void);
 

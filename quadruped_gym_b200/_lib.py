@@ -24,7 +24,13 @@ SYMBOLS = [
     "qg_last_error", "qg_version", "qg_model_load", "qg_model_destroy", "qg_model_info", "qg_batch_create",
     "qg_batch_destroy", "qg_batch_num_envs", "qg_set_options", "qg_set_reward_table", "qg_reset", "qg_step",
     "qg_step_host", "qg_get_state", "qg_set_state", "qg_debug_step", "qg_get_counters", "qg_launch_count",
-    "qg_fp32_peak",
+    "qg_fp32_peak", "qg_walk_enable", "qg_walk_reset", "qg_walk_set_commands", "qg_walk_get_commands", "qg_walk_step",
+]
+
+WALK_REWARD_KEYS = [  # WalkingQuadrupedEnv.reward_keys (/root/reference/src/envs/walking_quad.py:331-350)
+    "alive_bonus", "control_cost", "progress_direction_reward_local", "progress_speed_cost_local", "heading_reward",
+    "orientation_reward", "body_height_cost", "joint_posture_cost", "control_amplitude_cost", "control_frequency_cost",
+    "diff_ideal_position_cost",
 ]
 
 
@@ -76,6 +82,11 @@ def lib():
     L.qg_get_counters.argtypes = [vp, C.POINTER(Counters), i32, vp]
     L.qg_launch_count.restype = C.c_ulonglong
     L.qg_fp32_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]
+    L.qg_walk_enable.argtypes = [vp, i32, C.c_double, C.c_double, i32, C.c_double, i32, C.POINTER(C.c_double), C.POINTER(i32)]
+    L.qg_walk_reset.argtypes = [vp, u8p, i32, C.c_uint64, C.c_longlong, vp]
+    L.qg_walk_set_commands.argtypes = [vp, f64p, u8p, vp]
+    L.qg_walk_get_commands.argtypes = [vp, f64p, f64p, f64p, f64p, f64p, f64p, vp]
+    L.qg_walk_step.argtypes = [vp, f32p, f32p, u8p, f32p, f32p, f32p, f64p, f64p, i32, vp]
     _lib = L
     return L
 

@@ -11,7 +11,7 @@
 #include <vector>
 
 #include "../../include/quadgym.h"
-#include "qg_kernels.cuh"
+#include "qg_walk.cuh"
 
 static thread_local char g_err[512] = "";
 static unsigned long long g_launches = 0;
@@ -53,6 +53,11 @@ struct qg_batch {
     // pinned + device staging for the host-buffer path
     float *h_act, *h_obs, *h_rew, *d_act, *d_obs, *d_rew;
     unsigned char *h_term, *d_term;
+    // WalkingQuadrupedEnv reward stack (qg_walk_*)
+    bool walk_on;
+    QgWalkState walk;
+    QgWalkOpts wopts;
+    std::vector<void*> walk_allocs;
 };
 
 extern "C" const char* qg_last_error(void) { return g_err; }
@@ -452,7 +457,11 @@ extern "C" int qg_batch_create(const qg_model* m, int n_envs, int device, qg_bat
     if (device < 0 || device >= ndev) return fail(QG_EINVAL, "device %d out of range (%d devices)", device, ndev);
     CUDA_OK(cudaSetDevice(device));
     qg_batch* b = new qg_batch();
-    memset(b, 0, sizeof *b);
+    b->walk_on = false;
+    memset(&b->walk, 0, sizeof b->walk);
+    memset(&b->wopts, 0, sizeof b->wopts);
+    b->h_act = b->h_obs = b->h_rew = b->d_act = b->d_obs = b->d_rew = nullptr;
+    b->h_term = b->d_term = nullptr;
     b->n = n_envs;
     b->device = device;
     default_opts(m, b->opts);
@@ -498,6 +507,7 @@ extern "C" void qg_batch_destroy(qg_batch* b) {
     if (b->h_rew) cudaFreeHost(b->h_rew);
     if (b->h_term) cudaFreeHost(b->h_term);
     cudaFree(b->d_act); cudaFree(b->d_obs); cudaFree(b->d_rew); cudaFree(b->d_term);
+    for (void* p : b->walk_allocs) cudaFree(p);
     delete b;
 }
 
@@ -695,5 +705,98 @@ extern "C" int qg_fp32_peak(int device, int iters, double* tflops_out) {
     cudaEventDestroy(e1);
     cudaFree(out);
     *tflops_out = best;
+    return QG_OK;
+}
+
+// ------------------------------------------------------------------------------------------ walking env
+template <typename T>
+static int walk_alloc(qg_batch* b, T** p, size_t count) {
+    CUDA_OK(cudaMalloc(p, sizeof(T) * count));
+    CUDA_OK(cudaMemset(*p, 0, sizeof(T) * count));
+    b->walk_allocs.push_back(*p);
+    return QG_OK;
+}
+
+extern "C" int qg_walk_enable(qg_batch* b, int window, double dt, double timestep, int frame_skip, double settling_time,
+                              int random_controls, const double* sample_opts, const int* sample_has) {
+    if (!b || window < 1 || frame_skip < 1) return fail(QG_EINVAL, "qg_walk_enable: bad argument");
+    CUDA_OK(cudaSetDevice(b->device));
+    for (void* p : b->walk_allocs) cudaFree(p);
+    b->walk_allocs.clear();
+    QgWalkState& W = b->walk;
+    const size_t n = b->n;
+    W.n = b->n; W.window = window; W.dt = dt; W.timestep = timestep; W.frame_skip = frame_skip; W.ema_alpha = 0.80;
+    int rc = 0;
+    rc |= walk_alloc(b, &W.velocity, 3 * n); rc |= walk_alloc(b, &W.heading, 3 * n); rc |= walk_alloc(b, &W.global_velocity, 3 * n);
+    rc |= walk_alloc(b, &W.ideal_position, 3 * n); rc |= walk_alloc(b, &W.prev_derive, n); rc |= walk_alloc(b, &W.first_ctrl_cost, n);
+    rc |= walk_alloc(b, &W.prev_ctrl, 12 * n); rc |= walk_alloc(b, &W.signal_ring, (size_t)window * 12 * n);
+    rc |= walk_alloc(b, &W.cross_ring, (size_t)window * 12 * n); rc |= walk_alloc(b, &W.cross_count, 12 * n);
+    rc |= walk_alloc(b, &W.prev_sample, 12 * n); rc |= walk_alloc(b, &W.f_est, 12 * n); rc |= walk_alloc(b, &W.a_est, 12 * n);
+    rc |= walk_alloc(b, &W.prev_sign, 12 * n); rc |= walk_alloc(b, &W.buffer_index, n); rc |= walk_alloc(b, &W.sample_count, n);
+    rc |= walk_alloc(b, &W.flags, n); rc |= walk_alloc(b, &W.episode, n);
+    if (rc) return QG_ECUDA;
+    QgWalkOpts& o = b->wopts;
+    o.random_controls = random_controls;
+    o.auto_reset = 1;
+    o.seed = b->opts.seed;
+    o.env_offset = b->opts.env_offset;
+    o.min_speed = sample_opts ? sample_opts[0] : 0.0;
+    o.max_speed = sample_opts ? sample_opts[1] : 1.0;
+    o.fixed_heading = sample_opts ? sample_opts[2] : 0.0;
+    o.fixed_velocity_angle = sample_opts ? sample_opts[3] : 0.0;
+    o.fixed_speed = sample_opts ? sample_opts[4] : 0.0;
+    o.has_heading = sample_has ? sample_has[0] : 0;
+    o.has_velocity_angle = sample_has ? sample_has[1] : 0;
+    o.has_speed = sample_has ? sample_has[2] : 0;
+    for (int i = 0; i < 12; ++i) o.joint_centers[i] = b->opts.reset_ctrl[i];   // walking_quad.py:36-39 == quadruped.py:124
+    b->opts.settling_time = settling_time;
+    b->walk_on = true;
+    return qg_walk_reset(b, nullptr, 1, 0, 0, nullptr);
+}
+
+extern "C" int qg_walk_reset(qg_batch* b, const uint8_t* mask_dev, int hard, uint64_t seed, long long env_offset, void* stream) {
+    if (!b || !b->walk_on) return fail(QG_EINVAL, "qg_walk_reset: walking mode is not enabled");
+    CUDA_OK(cudaSetDevice(b->device));
+    if (hard) { b->wopts.seed = seed; b->wopts.env_offset = env_offset; }
+    qg_walk_reset_kernel<<<(b->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->walk, b->wopts, mask_dev, hard);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return QG_OK;
+}
+
+extern "C" int qg_walk_set_commands(qg_batch* b, const double* speed_alpha_theta_dev, const uint8_t* mask_dev, void* stream) {
+    if (!b || !b->walk_on || !speed_alpha_theta_dev) return fail(QG_EINVAL, "qg_walk_set_commands: bad argument");
+    CUDA_OK(cudaSetDevice(b->device));
+    qg_walk_set_commands_kernel<<<(b->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->walk, speed_alpha_theta_dev, mask_dev);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return QG_OK;
+}
+
+extern "C" int qg_walk_get_commands(qg_batch* b, double* velocity_dev, double* heading_dev, double* global_velocity_dev,
+                                    double* ideal_position_dev, double* f_est_dev, double* a_est_dev, void* stream) {
+    if (!b || !b->walk_on) return fail(QG_EINVAL, "qg_walk_get_commands: walking mode is not enabled");
+    CUDA_OK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = b->n;
+    if (velocity_dev) CUDA_OK(cudaMemcpyAsync(velocity_dev, b->walk.velocity, 3 * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (heading_dev) CUDA_OK(cudaMemcpyAsync(heading_dev, b->walk.heading, 3 * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (global_velocity_dev) CUDA_OK(cudaMemcpyAsync(global_velocity_dev, b->walk.global_velocity, 3 * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (ideal_position_dev) CUDA_OK(cudaMemcpyAsync(ideal_position_dev, b->walk.ideal_position, 3 * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (f_est_dev) CUDA_OK(cudaMemcpyAsync(f_est_dev, b->walk.f_est, 12 * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (a_est_dev) CUDA_OK(cudaMemcpyAsync(a_est_dev, b->walk.a_est, 12 * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return QG_OK;
+}
+
+extern "C" int qg_walk_step(qg_batch* b, float* obs_dev, const float* ctrl_dev, const uint8_t* terminated_dev,
+                            float* terminal_obs_dev, float* reward_dev, float* terms_dev, double* reward64_dev,
+                            double* terms64_dev, int auto_reset, void* stream) {
+    if (!b || !b->walk_on || !obs_dev) return fail(QG_EINVAL, "qg_walk_step: bad argument");
+    CUDA_OK(cudaSetDevice(b->device));
+    b->wopts.auto_reset = auto_reset;
+    qg_walk_kernel<<<(b->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->walk, b->wopts, obs_dev, ctrl_dev, b->d_state, terminated_dev,
+                                                                          terminal_obs_dev, reward_dev, terms_dev, reward64_dev, terms64_dev);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
     return QG_OK;
 }

@@ -173,6 +173,7 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
         for (int k = 0; k < 3; ++k) {
             float a = action[(size_t)env * 12 + 3 * leg + k];
             if (clip_action) a = fminf(fmaxf(a, -1.f), 1.f);
+            if (L.time < opts.settling_time) a = opts.reset_ctrl[3 * leg + k];
             L.ctrl[k] = a;
         }
 

@@ -90,6 +90,7 @@ struct QgStepOpts {
     double max_time;
     int flip_termination, auto_reset, max_iter, ls_iter;
     int random_yaw;
+    double settling_time;   // data.time < settling_time -> action := joint centres (walking_quad.py:142-143)
     unsigned long long seed;
     long long env_offset;
     float reset_ctrl[12];

@@ -67,3 +67,87 @@ def flip_termination(obs):                         # walking_quad.py:152-156
 
 def time_limit(time, max_time):                    # quadruped.py:149-151
     return time >= max_time
+
+
+class WalkingRewardRef:
+    """WalkingQuadrupedEnv.step bookkeeping + input_control_reward (walking_quad.py:128-148,352-422) with the
+    estimator of math_utils.py:11-133, restated for one environment."""
+
+    def __init__(self, timestep=0.002, frame_skip=4, velocity=(0, 0, 0), heading=(0, 0, 0), global_velocity=(0, 0, 0)):
+        self.timestep, self.frame_skip = timestep, frame_skip
+        self.dt = timestep * frame_skip
+        self.window = int(np.ceil(2 / (1 * self.dt)))
+        self.velocity, self.heading = np.array(velocity, dtype=float), np.array(heading, dtype=float)
+        self.global_velocity = np.array(global_velocity, dtype=float)
+        self.ideal_position = np.zeros(3)
+        self.cc = ControlCost()
+        self.prev_derive = None
+        self.prev_ctrl_for_estimator = JOINT_CENTERS.astype(np.float64)      # data.ctrl after reset
+        n = 12
+        self.cross_buf = np.zeros((self.window, n), dtype=int)
+        self.sig_buf = np.zeros((self.window, n))
+        self.idx, self.cross_count, self.sample_count = 0, np.zeros(n, dtype=int), 0
+        self.prev_sample, self.prev_sign = None, None
+        self.f_est, self.a_est = np.zeros(n), np.zeros(n)
+
+    def reset(self):                                  # walking_quad.py:96-126 (estimator and first cost survive)
+        self.ideal_position = np.zeros(3)
+        self.cc.reset()
+        self.prev_derive = None
+        self.prev_ctrl_for_estimator = JOINT_CENTERS.astype(np.float64)
+
+    def _estimator_update(self, x):
+        x = np.asarray(x, dtype=float)
+        if self.prev_sample is None:
+            self.prev_sample = x.copy()
+            self.sig_buf[self.idx] = x
+            self.sample_count = 1
+            self.idx = (self.idx + 1) % self.window
+            return
+        diff = x - self.prev_sample
+        sign = np.sign(diff)
+        if self.prev_sign is not None:
+            z = sign == 0
+            sign[z] = self.prev_sign[z]
+            crossing = (sign != self.prev_sign).astype(int)
+        else:
+            crossing = np.zeros(12, dtype=int)
+        if self.sample_count < self.window:
+            self.sample_count += 1
+        self.cross_count -= self.cross_buf[self.idx]
+        self.cross_buf[self.idx] = crossing
+        self.cross_count += crossing
+        self.sig_buf[self.idx] = x
+        self.idx = (self.idx + 1) % self.window
+        self.prev_sample, self.prev_sign = x.copy(), sign.copy()
+        f_cur = (self.cross_count / 2.0) / (self.sample_count * self.dt)
+        self.f_est = 0.8 * self.f_est + (1 - 0.8) * f_cur
+        w = self.sig_buf[: self.sample_count] if self.sample_count < self.window else self.sig_buf
+        self.a_est = 0.8 * self.a_est + (1 - 0.8) * (np.max(w, axis=0) - np.min(w, axis=0))
+
+    def step(self, obs, ctrl):
+        """obs / ctrl AFTER the physics of this env.step(); returns (total, 11 values)."""
+        self.ideal_position = self.ideal_position + self.global_velocity * self.timestep * self.frame_skip
+        self._estimator_update(self.prev_ctrl_for_estimator)
+        self.prev_ctrl_for_estimator = np.asarray(ctrl, dtype=float).copy()
+        unit = lambda x: x / np.linalg.norm(x)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            body_vel, cmd = obs[30:32], self.velocity[:2]
+            vals = [
+                10.0 * 1,
+                -2.0 * self.cc(np.asarray(ctrl, dtype=float)),
+                10.0 * np.dot(unit(body_vel), unit(cmd)),
+                -50.0 * np.square(np.linalg.norm(body_vel) - np.linalg.norm(cmd)),
+                10.0 * exp_dist(np.dot(obs[24:26], self.heading[:2])),
+                10.0 * exp_dist(obs[29]),
+                -50.0 * exp_dist(np.abs(obs[20] - 0.13)),
+                -1.0 * np.linalg.norm((ctrl - JOINT_CENTERS) / 12),
+                -2.5 * np.linalg.norm((self.a_est - np.array([1.5, 0.5, 0.0] * 4, dtype=np.float32)) / 12),
+                -8.0 * np.linalg.norm((self.f_est - np.array([1.0, 1.0, 0.0] * 4, dtype=np.float32)) / 12),
+            ]
+        r = -20.0 * np.linalg.norm(obs[18:20] - self.ideal_position[:2])
+        if self.prev_derive is None:
+            self.prev_derive = r
+        vals.append((r - self.prev_derive) / (self.timestep * self.frame_skip))
+        self.prev_derive = r
+        return sum(np.array(vals)), np.array(vals)

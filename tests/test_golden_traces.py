@@ -58,6 +58,16 @@ def test_trace_C_fused_terms_match_reference_values():
         assert (obs[29] < 0) == G["C_terminated"][t] or G["C_terminated"][t] == (obs[29] < 0)
 
 
+def test_trace_C_full_walking_reward_stack_restatement():
+    """tests/ref_formulas.WalkingRewardRef (ideal position, estimator, 11 terms, Python sum) == the reference's
+    WalkingQuadrupedEnv on every step of trace C, bit for bit."""
+    w = F.WalkingRewardRef(velocity=G["C_cmd_velocity"], heading=G["C_cmd_heading"], global_velocity=G["C_global_velocity"])
+    assert w.window == 250
+    for t in range(len(G["C_obs"])):
+        total, vals = w.step(G["C_obs"][t], G["C_ctrl"][t])
+        assert np.array_equal(vals, G["C_terms"][t]) and total == G["C_reward"][t]
+
+
 @pytest.mark.parametrize("tag", ["D80", "D95"])
 def test_trace_D_flip_termination(oracle_model, tag):
     d = OracleData(oracle_model)

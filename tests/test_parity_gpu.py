@@ -350,3 +350,81 @@ def test_single_env_shim_matches_reference_signature(Vec):
     env.close()
     with pytest.raises(FileNotFoundError):
         QuadrupedEnv(model_path="/nonexistent/scene.xml")        # quadruped.py:55-56
+
+
+def test_walking_reward_stack_against_reference_trace(Vec):
+    """Golden trace C (the reference's WalkingQuadrupedEnv): the device walking kernel fed the trace's sensordata
+    (cast to float32, as the step kernel produces it) and ctrl reproduces all 11 reward terms, the total and the
+    estimator state of the numpy restatement evaluated on the same float32 inputs.  Tolerance 1e-12 relative
+    (float64 exp / sqrt / fused multiply-adds differ from numpy in the last bits); alive / time are exact."""
+    import ctypes as C
+    from quadruped_gym_b200 import _lib
+    from quadruped_gym_b200.envs.walking_quad import VecWalkingQuadrupedEnv
+    n = 4
+    env = VecWalkingQuadrupedEnv(n, "cuda:0", auto_reset=False)
+    env.reset()
+    env.control_inputs.set_speed_alpha_theta(0.3, 0.1, 0.3)     # trace C: set_orientation(0.3), speed 0.3 / alpha 0.1
+    assert np.allclose(env.control_inputs.velocity[0].cpu().numpy(), G["C_cmd_velocity"], atol=1e-15)
+    assert np.allclose(env.control_inputs.global_velocity[0].cpu().numpy(), G["C_global_velocity"], atol=1e-15)
+    ref = F.WalkingRewardRef(velocity=env.control_inputs.velocity[0].cpu().numpy(), heading=env.control_inputs.heading[0].cpu().numpy(),
+                             global_velocity=env.control_inputs.global_velocity[0].cpu().numpy())
+    r64 = torch.zeros(n, dtype=torch.float64, device="cuda")
+    t64 = torch.zeros((n, 11), dtype=torch.float64, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    for t in range(len(G["C_obs"])):
+        obs32 = G["C_obs"][t].astype(np.float32)
+        obs = torch.from_numpy(np.tile(obs32, (n, 1))).cuda().contiguous()
+        ctrl = torch.from_numpy(np.tile(G["C_ctrl"][t].astype(np.float32), (n, 1))).cuda().contiguous()
+        _lib.check(_lib.lib().qg_walk_step(env._batch, p(obs), p(ctrl), None, None, None, None, p(r64), p(t64), 0, None))
+        total, vals = ref.step(obs32.astype(np.float64), G["C_ctrl"][t])
+        got = t64[0].cpu().numpy()
+        assert got[0] == vals[0] == 10.0
+        assert np.allclose(got[:10], vals[:10], rtol=1e-12, atol=1e-13), (t, got - vals)
+        # the 11th term is a finite difference (r - r_prev)/0.008 of values ~1: last-bit differences are amplified
+        assert abs(got[10] - vals[10]) <= 1e-11 * max(1.0, abs(vals[10]))
+        assert r64[0].item() == pytest.approx(total, rel=1e-12, abs=1e-11)
+        assert abs(r64[0].item() - G["C_reward"][t]) < 1e-4 * max(1.0, abs(G["C_reward"][t]))   # vs the float64-obs reference
+        assert torch.equal(t64[0], t64[n - 1])
+    assert np.allclose(env.ctrl_f_est[0].cpu().numpy(), ref.f_est, rtol=1e-13, atol=1e-15)
+    assert np.allclose(env.ctrl_a_est[0].cpu().numpy(), ref.a_est, rtol=1e-13, atol=1e-15)
+    assert np.allclose(env.ideal_position[0].cpu().numpy(), ref.ideal_position, rtol=1e-14)
+    env.close()
+
+
+def test_walking_env_end_to_end(Vec):
+    """VecWalkingQuadrupedEnv rollout: reward / info terms equal the restatement applied to the device's own
+    sensordata and ctrl; flip / time-limit termination; reset bookkeeping (ideal position, derivative memory,
+    command resampling with random_controls); settling mask."""
+    from quadruped_gym_b200.envs.walking_quad import VecWalkingQuadrupedEnv
+    n = 6
+    env = VecWalkingQuadrupedEnv(n, "cuda:0", auto_reset=True, max_time=0.4, settling_time=0.05, random_controls=True,
+                                 reset_options={"fixed_heading_angle": 0.0, "fixed_velocity_angle": 0.0, "fixed_speed": 0.3})
+    obs, info = env.reset()
+    assert info == {} and torch.count_nonzero(obs) == 0
+    v0 = env.control_inputs.velocity.cpu().numpy()
+    assert np.allclose(v0, np.tile([0.3, 0.0, 0.0], (n, 1)))                 # fixed_* options (train_quadruped.py:40-46)
+    refs = [F.WalkingRewardRef(velocity=v0[e], heading=env.control_inputs.heading[e].cpu().numpy(),
+                               global_velocity=env.control_inputs.global_velocity[e].cpu().numpy()) for e in range(n)]
+    rng = np.random.default_rng(4)
+    saw_term = False
+    for t in range(70):
+        a = rng.uniform(-1, 1, (n, 12)).astype(np.float32)
+        time_before = env.data.time.cpu().numpy()
+        obs, rew, term, trunc, info = env.step(torch.from_numpy(a).cuda())
+        sens = env.data.sensordata.cpu().numpy().astype(np.float64)         # last forward pass, also for reset envs
+        for e in range(n):
+            applied = np.where(time_before[e] < 0.05, np.array([0, 0, -0.5] * 4, np.float32), a[e])   # settling mask
+            total, vals = refs[e].step(sens[e], applied.astype(np.float64))
+            got = np.array([info[k][e].item() for k in env.reward_keys])
+            assert np.allclose(got, vals.astype(np.float32), rtol=2e-6, atol=1e-6), (t, e)
+            assert rew[e].item() == pytest.approx(np.float32(total), rel=2e-6, abs=1e-5)
+            want_term = (time_before[e] + 4 * 0.002 >= 0.4 - 1e-12) or sens[e][29] < 0
+            assert bool(term[e]) == bool(want_term)
+            if term[e]:
+                saw_term = True
+                refs[e].reset()
+                assert torch.count_nonzero(obs[e]) == 0 and float(env.data.time[e]) == 0.0
+                assert np.array_equal(env.ideal_position[e].cpu().numpy(), np.zeros(3))
+        assert set(env.reward_keys) <= set(info)
+    assert saw_term
+    env.close()
