@@ -175,6 +175,18 @@ int qg_walk_step(qg_batch* b, float* obs_dev, const float* ctrl_dev, const uint8
                  float* terminal_obs_dev, float* reward_dev, float* terms_dev, double* reward64_dev,
                  double* terms64_dev, int auto_reset, void* stream);
 
+/* --- POWalkingQuadrupedEnv observation (src/envs/po_walking_quad.py:8-90) -----------------------------------
+ * 26 values per frame (gyro, accel, Madgwick-filter Euler angles, body_vel xy, ctrl, command velocity xy, heading
+ * angle), FIFO-stacked over obs_window frames -> stacked_dev [N, 26*obs_window] f32, oldest frame first.
+ * Dt = timestep*frame_skip (po_walking_quad.py:18), beta = Madgwick IMU gain (ahrs default 0.033).
+ * qg_po_observe(is_reset_call = 0) runs after qg_step + qg_walk_step and before the masked qg_reset of a step;
+ * sensordata_dev is that step's sensordata (the terminal one for terminated envs).  is_reset_call = 1 fills the
+ * stack of the masked envs (terminated_dev as mask, NULL = all) with the reset frame (po_walking_quad.py:59-70). */
+#define QG_PO_FRAME 26
+int qg_po_enable(qg_batch* b, int obs_window, double Dt, double beta, double settling_time);
+int qg_po_observe(qg_batch* b, const float* sensordata_dev, const uint8_t* terminated_dev, float* stacked_dev,
+                  float* terminal_stacked_dev, int auto_reset, int is_reset_call, void* stream);
+
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 unsigned long long qg_launch_count(void);
 

@@ -25,6 +25,7 @@ SYMBOLS = [
     "qg_batch_destroy", "qg_batch_num_envs", "qg_set_options", "qg_set_reward_table", "qg_reset", "qg_step",
     "qg_step_host", "qg_get_state", "qg_set_state", "qg_debug_step", "qg_get_counters", "qg_launch_count",
     "qg_fp32_peak", "qg_walk_enable", "qg_walk_reset", "qg_walk_set_commands", "qg_walk_get_commands", "qg_walk_step",
+    "qg_po_enable", "qg_po_observe",
 ]
 
 WALK_REWARD_KEYS = [  # WalkingQuadrupedEnv.reward_keys (/root/reference/src/envs/walking_quad.py:331-350)
@@ -87,6 +88,8 @@ def lib():
     L.qg_walk_set_commands.argtypes = [vp, f64p, u8p, vp]
     L.qg_walk_get_commands.argtypes = [vp, f64p, f64p, f64p, f64p, f64p, f64p, vp]
     L.qg_walk_step.argtypes = [vp, f32p, f32p, u8p, f32p, f32p, f32p, f64p, f64p, i32, vp]
+    L.qg_po_enable.argtypes = [vp, i32, C.c_double, C.c_double, C.c_double]
+    L.qg_po_observe.argtypes = [vp, f32p, u8p, f32p, f32p, i32, i32, vp]
     _lib = L
     return L
 

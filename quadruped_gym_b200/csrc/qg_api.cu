@@ -58,6 +58,8 @@ struct qg_batch {
     QgWalkState walk;
     QgWalkOpts wopts;
     std::vector<void*> walk_allocs;
+    bool po_on;
+    QgPoState po;
 };
 
 extern "C" const char* qg_last_error(void) { return g_err; }
@@ -458,6 +460,8 @@ extern "C" int qg_batch_create(const qg_model* m, int n_envs, int device, qg_bat
     CUDA_OK(cudaSetDevice(device));
     qg_batch* b = new qg_batch();
     b->walk_on = false;
+    b->po_on = false;
+    memset(&b->po, 0, sizeof b->po);
     memset(&b->walk, 0, sizeof b->walk);
     memset(&b->wopts, 0, sizeof b->wopts);
     b->h_act = b->h_obs = b->h_rew = b->d_act = b->d_obs = b->d_rew = nullptr;
@@ -796,6 +800,32 @@ extern "C" int qg_walk_step(qg_batch* b, float* obs_dev, const float* ctrl_dev, 
     b->wopts.auto_reset = auto_reset;
     qg_walk_kernel<<<(b->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->walk, b->wopts, obs_dev, ctrl_dev, b->d_state, terminated_dev,
                                                                           terminal_obs_dev, reward_dev, terms_dev, reward64_dev, terms64_dev);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return QG_OK;
+}
+
+// ------------------------------------------------------------------------------------------ partially observable env
+extern "C" int qg_po_enable(qg_batch* b, int obs_window, double Dt, double beta, double settling_time) {
+    if (!b || !b->walk_on || obs_window < 1) return fail(QG_EINVAL, "qg_po_enable: enable the walking stack first (qg_walk_enable)");
+    CUDA_OK(cudaSetDevice(b->device));
+    QgPoState& P = b->po;
+    P.n = b->n; P.window = obs_window; P.Dt = Dt; P.beta = beta; P.settle_half = settling_time / 2;
+    if (walk_alloc(b, &P.q, 4 * (size_t)b->n) || walk_alloc(b, &P.is_view, (size_t)b->n)) return QG_ECUDA;
+    std::vector<double> q0(4 * (size_t)b->n, 0.0);
+    for (int i = 0; i < b->n; ++i) q0[4 * (size_t)i] = 1.0;      // computed_orientation = [1, 0, 0, 0] (po_walking_quad.py:19)
+    CUDA_OK(cudaMemcpy(P.q, q0.data(), q0.size() * sizeof(double), cudaMemcpyHostToDevice));
+    b->po_on = true;
+    return QG_OK;
+}
+
+extern "C" int qg_po_observe(qg_batch* b, const float* sensordata_dev, const uint8_t* terminated_dev, float* stacked_dev,
+                             float* terminal_stacked_dev, int auto_reset, int is_reset_call, void* stream) {
+    if (!b || !b->po_on || !stacked_dev || (!is_reset_call && !sensordata_dev)) return fail(QG_EINVAL, "qg_po_observe: bad argument");
+    CUDA_OK(cudaSetDevice(b->device));
+    qg_po_kernel<<<(b->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->po, b->walk, b->wopts, sensordata_dev ? sensordata_dev : stacked_dev,
+                                                                        b->d_state, terminated_dev, stacked_dev, terminal_stacked_dev,
+                                                                        auto_reset, is_reset_call);
     g_launches++;
     CUDA_OK(cudaGetLastError());
     return QG_OK;

@@ -242,3 +242,116 @@ __global__ void qg_walk_set_commands_kernel(QgWalkState W, const double* __restr
     gv[1] = hd[1] * v[0] + hd[0] * v[1];
     gv[2] = 0.0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// POWalkingQuadrupedEnv observation (/root/reference/src/envs/po_walking_quad.py:29-90): Madgwick IMU filter ->
+// Euler angles, 26 values per frame (gyro 3, accel 3, euler 3, body_vel xy 2, ctrl 12, command velocity xy 2,
+// heading angle 1), FIFO-stacked over obs_window frames (oldest first).
+// The filter lives in the third-party package `ahrs` (not vendored, not installable here): updateIMU and
+// Quaternion.to_angles are restated from its published algorithm -- PARITY UNPINNED.
+#define QG_PO_FRAME 26
+
+struct QgPoState {
+    int n, window;
+    double Dt, beta, settle_half;   // timestep*frame_skip, Madgwick gain (0.033 for the IMU variant), settling_time/2
+    double* q;                      // [N,4] computed_orientation
+    int* is_view;                   // [N] computed_orientation aliases data.qpos[3:7] (po_walking_quad.py:68)
+};
+
+DI void madgwick_update_imu(double* q, const double* g, const double* a, double Dt, double beta) {
+    double gn = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+    if (gn == 0.0) return;
+    double qw = q[0], qx = q[1], qy = q[2], qz = q[3];
+    // qDot = 0.5 * q (x) (0, gyr)
+    double dw = 0.5 * (-qx * g[0] - qy * g[1] - qz * g[2]);
+    double dx = 0.5 * (qw * g[0] + qy * g[2] - qz * g[1]);
+    double dy = 0.5 * (qw * g[1] - qx * g[2] + qz * g[0]);
+    double dz = 0.5 * (qw * g[2] + qx * g[1] - qy * g[0]);
+    double an = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    if (an > 0.0) {
+        double ax = a[0] / an, ay = a[1] / an, az = a[2] / an;
+        double qn = sqrt(qw * qw + qx * qx + qy * qy + qz * qz);
+        double w = qw / qn, x = qx / qn, y = qy / qn, z = qz / qn;
+        double f0 = 2.0 * (x * z - w * y) - ax, f1 = 2.0 * (w * x + y * z) - ay, f2 = 2.0 * (0.5 - x * x - y * y) - az;
+        if (sqrt(f0 * f0 + f1 * f1 + f2 * f2) > 0.0) {
+            // gradient = J^T f
+            double g0 = -2.0 * y * f0 + 2.0 * x * f1;
+            double g1 = 2.0 * z * f0 + 2.0 * w * f1 - 4.0 * x * f2;
+            double g2 = -2.0 * w * f0 + 2.0 * z * f1 - 4.0 * y * f2;
+            double g3 = 2.0 * x * f0 + 2.0 * y * f1;
+            double gnorm = sqrt(g0 * g0 + g1 * g1 + g2 * g2 + g3 * g3);
+            dw -= beta * g0 / gnorm; dx -= beta * g1 / gnorm; dy -= beta * g2 / gnorm; dz -= beta * g3 / gnorm;
+        }
+    }
+    qw += dw * Dt; qx += dx * Dt; qy += dy * Dt; qz += dz * Dt;
+    double n = sqrt(qw * qw + qx * qx + qy * qy + qz * qz);
+    q[0] = qw / n; q[1] = qx / n; q[2] = qy / n; q[3] = qz / n;
+}
+
+DI void po_frame(const QgPoState& P, const QgWalkState& W, int e, const float* s, const double* ctrl, const double* q, float* out) {
+    // Quaternion.to_angles(): roll, pitch, yaw
+    double w = q[0], x = q[1], y = q[2], z = q[3];
+    double roll = atan2(2.0 * (w * x + y * z), 1.0 - 2.0 * (x * x + y * y));
+    double sp = 2.0 * (w * y - z * x);
+    double pitch = asin(fmin(1.0, fmax(-1.0, sp)));
+    double yaw = atan2(2.0 * (w * z + x * y), 1.0 - 2.0 * (y * y + z * z));
+    out[0] = s[15]; out[1] = s[16]; out[2] = s[17];          // gyro
+    out[3] = s[12]; out[4] = s[13]; out[5] = s[14];          // accel
+    out[6] = (float)roll; out[7] = (float)pitch; out[8] = (float)yaw;
+    out[9] = s[30]; out[10] = s[31];                         // body_vel xy (optical flow)
+    for (int k = 0; k < 12; ++k) out[11 + k] = (float)ctrl[k];
+    const double* v = W.velocity + 3 * (size_t)e;
+    const double* hd = W.heading + 3 * (size_t)e;
+    out[23] = (float)v[0]; out[24] = (float)v[1];
+    out[25] = (float)atan2(hd[1], hd[0]);                    // get_heading_theta
+}
+
+// After the physics + walking launches of one step (and BEFORE the masked physics reset):
+//   sens = sensordata of this step (terminal one for terminated envs), S = state planes (post-step, pre-reset),
+//   stacked [N, 26*window] is shifted by one frame and the new frame appended; terminated envs get their
+//   terminal stack copied to terminal_stacked and are re-filled with the reset frame (po_walking_quad.py:59-70).
+__global__ void qg_po_kernel(QgPoState P, QgWalkState W, QgWalkOpts o, const float* __restrict__ sens, const float4* __restrict__ S,
+                             const unsigned char* __restrict__ terminated, float* __restrict__ stacked,
+                             float* __restrict__ terminal_stacked, int auto_reset, int is_reset_call) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = P.n;
+    if (e >= N) return;
+    const int F = QG_PO_FRAME, Wn = P.window;
+    float* st = stacked + (size_t)e * F * Wn;
+    double* q = P.q + 4 * (size_t)e;
+    const float* s = sens + (size_t)e * 33;
+    float4 tq = S[(size_t)QG_PL_TIME * N + e];
+    double time = __hiloint2double(__float_as_int(tq.y), __float_as_int(tq.x));
+    float4 bq = S[(size_t)QG_PL_QUAT * N + e];
+    double ctrl[12];
+    for (int l = 0; l < 4; ++l) {
+        float4 c = S[(size_t)(QG_PL_LEG0 + 4 * l + 3) * N + e];
+        ctrl[3 * l] = c.x; ctrl[3 * l + 1] = c.y; ctrl[3 * l + 2] = c.z;
+    }
+    float frame[QG_PO_FRAME];
+    if (!is_reset_call) {
+        if (P.is_view[e]) { q[0] = bq.x; q[1] = bq.y; q[2] = bq.z; q[3] = bq.w; }
+        if (time > P.settle_half) {
+            double g[3] = {s[15], s[16], s[17]}, a[3] = {s[12], s[13], s[14]};
+            madgwick_update_imu(q, g, a, P.Dt, P.beta);
+            P.is_view[e] = 0;   // updateIMU returns a new array: the alias to qpos is gone
+        }
+        po_frame(P, W, e, s, ctrl, q, frame);
+        for (int k = 0; k < F * (Wn - 1); ++k) st[k] = st[k + F];
+        for (int k = 0; k < F; ++k) st[F * (Wn - 1) + k] = frame[k];
+    }
+    const bool term = is_reset_call ? (!terminated || terminated[e]) : (terminated && terminated[e]);
+    if (!is_reset_call && terminal_stacked)
+        for (int k = 0; k < F * Wn; ++k) terminal_stacked[(size_t)e * F * Wn + k] = term ? st[k] : 0.f;
+    if (term && (auto_reset || is_reset_call)) {
+        // reset(): sensordata zero, ctrl = joint centres, orientation still the stale filter state, commands not yet resampled
+        float zero[33];
+        for (int k = 0; k < 33; ++k) zero[k] = 0.f;
+        double c0[12];
+        for (int k = 0; k < 12; ++k) c0[k] = (double)o.joint_centers[k];
+        po_frame(P, W, e, zero, c0, q, frame);
+        for (int w = 0; w < Wn; ++w)
+            for (int k = 0; k < F; ++k) st[w * F + k] = frame[k];
+        P.is_view[e] = 1;   // computed_orientation = data.qpos[3:7]
+    }
+}

@@ -1,0 +1,138 @@
+"""Vectorised POWalkingQuadrupedEnv (/root/reference/src/envs/po_walking_quad.py:8-90) and an SB3-style VecEnv
+adapter, so that the reference's training / evaluation scripts can swap their ``SubprocVecEnv([...]*10)``
+(/root/reference/src/train_quadruped.py:49-50) for N device-resident environments.
+
+Observation per frame (26): gyro, accel, Euler angles of a Madgwick IMU filter, body_vel xy, ctrl, command
+velocity xy, heading angle -- stacked over ``obs_window`` frames.  The filter is ``ahrs``' (third party, not
+installable here): restated from its published algorithm, parity unpinned.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .quadruped import _box, _ptr
+from .walking_quad import VecWalkingQuadrupedEnv
+
+
+class VecPOWalkingQuadrupedEnv(VecWalkingQuadrupedEnv):
+    FRAME = 26
+
+    def __init__(self, num_envs: int = 1, device="cuda:0", obs_window: int = 1, madgwick_gain: float = 0.033, **kwargs):
+        super().__init__(num_envs=num_envs, device=device, **kwargs)
+        self.obs_window = int(obs_window)
+        _lib.check(_lib.lib().qg_po_enable(self._batch, self.obs_window, self.dt, float(madgwick_gain), self.settling_time), "qg_po_enable")
+        d = self.FRAME * self.obs_window                                       # po_walking_quad.py:22-27
+        self.observation_space = _box(-np.inf, np.inf, (d,))
+        self._stacked = torch.zeros((self.num_envs, d), dtype=torch.float32, device=self.device)
+        self._term_stacked = torch.zeros((self.num_envs, d), dtype=torch.float32, device=self.device)
+
+    def reset(self, seed=None, options=None, mask: Optional[torch.Tensor] = None):
+        m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        # the reset observation is built inside the base reset, i.e. BEFORE command resampling (quadruped.py:138
+        # runs inside walking_quad.py:103): fill the stack first, then do the walking / physics reset
+        super(VecWalkingQuadrupedEnv, self).reset(seed=seed, options=options, mask=mask)
+        _lib.check(_lib.lib().qg_po_observe(self._batch, None, _ptr(m), _ptr(self._stacked), None, 1, 1, self._stream()), "qg_po_observe")
+        _lib.check(_lib.lib().qg_walk_reset(self._batch, _ptr(m), 0, self.seed_value, self.env_offset, self._stream()), "qg_walk_reset")
+        self.info = {}
+        return self._stacked, self.info
+
+    def step(self, action: torch.Tensor):
+        L = _lib.lib()
+        if self._table_key != "walking":
+            _lib.check(L.qg_set_reward_table(self._batch, 0, None, None, None), "qg_set_reward_table")
+            _lib.check(L.qg_set_options(self._batch, self.max_time, 1, 0, 0, 0), "qg_set_options")
+            self._table_key = "walking"
+        a = torch.as_tensor(action, device=self.device, dtype=torch.float32).reshape(self.num_envs, 12).contiguous()
+        st = self._stream()
+        _lib.check(L.qg_step(self._batch, _ptr(a), self.frame_skip, _ptr(self._obs), _ptr(self._reward), None,
+                             _ptr(self._terminated), None, st), "qg_step")
+        _lib.check(L.qg_po_observe(self._batch, _ptr(self._obs), _ptr(self._terminated), _ptr(self._stacked),
+                                   _ptr(self._term_stacked), int(self.auto_reset), 0, st), "qg_po_observe")
+        _lib.check(L.qg_walk_step(self._batch, _ptr(self._obs), None, _ptr(self._terminated), _ptr(self._term_obs),
+                                  _ptr(self._reward), _ptr(self._wterms), _ptr(self._wrew64), _ptr(self._wterms64),
+                                  int(self.auto_reset), st), "qg_walk_step")
+        if self.auto_reset:
+            _lib.check(L.qg_reset(self._batch, _ptr(self._terminated), self.seed_value, int(self.random_init), self.env_offset, st), "qg_reset")
+        terminated = self._terminated.bool()
+        self._last_sensordata = torch.where(terminated[:, None], self._term_obs, self._obs) if self.auto_reset else self._obs
+        self.info = {k: self._wterms[:, i] for i, k in enumerate(self.reward_keys)}
+        self.info["terminal_observation"] = self._term_stacked
+        return self._stacked, self._reward, terminated, torch.zeros_like(terminated), self.info
+
+
+class SB3VecEnvAdapter:
+    """stable-baselines3 ``VecEnv`` surface over a vectorised env of this package: numpy in / numpy out, one D2H
+    copy per step, same-step auto-reset with ``infos[i]["terminal_observation"]`` and ``"TimeLimit.truncated"``,
+    and the 11 reward keys in every info dict (RewardCallback._on_step indexes them unconditionally,
+    /root/reference/src/train_quadruped.py:86-92).  Duck-typed: SB3 itself is not required (nor installed here)."""
+
+    def __init__(self, env):
+        if not env.auto_reset:
+            raise ValueError("SB3 VecEnv semantics need auto_reset=True")
+        self.env = env
+        self.num_envs = env.num_envs
+        self.observation_space, self.action_space = env.observation_space, env.action_space
+        self.render_mode = None
+        self._actions = None
+        self.reward_keys = list(getattr(env, "reward_keys", []))
+
+    def reset(self):
+        obs, _ = self.env.reset()
+        return obs.cpu().numpy()
+
+    def step_async(self, actions):
+        self._actions = np.asarray(actions, dtype=np.float32)
+
+    def step_wait(self):
+        obs, rew, term, trunc, info = self.env.step(torch.from_numpy(self._actions))
+        # one packed D2H transfer: obs | reward | done | per-term rewards
+        keys = self.reward_keys
+        terms = torch.stack([info[k] for k in keys], dim=1) if keys else torch.zeros((self.num_envs, 0), device=obs.device)
+        packed = torch.cat([obs, rew[:, None], term[:, None].float(), terms], dim=1).cpu().numpy()
+        d = obs.shape[1]
+        o, r, done, tv = packed[:, :d], packed[:, d], packed[:, d + 1] > 0.5, packed[:, d + 2:]
+        tobs = info["terminal_observation"][term].cpu().numpy() if done.any() else None
+        infos: List[dict] = []
+        j = 0
+        for i in range(self.num_envs):
+            di = {k: float(tv[i, c]) for c, k in enumerate(keys)}
+            di["TimeLimit.truncated"] = False        # the reference reports the time limit as terminated
+            if done[i]:
+                di["terminal_observation"] = tobs[j]
+                j += 1
+            infos.append(di)
+        return o.copy(), r.copy(), done, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self):
+        self.env.close()
+
+    def seed(self, seed=None):
+        return [self.env.seed(seed)] * self.num_envs
+
+    def get_attr(self, name, indices=None):
+        n = self.num_envs if indices is None else len(list(indices))
+        return [getattr(self.env, name)] * n
+
+    def set_attr(self, name, value, indices=None):
+        setattr(self.env, name, value)
+
+    def env_method(self, method_name, *args, indices=None, **kwargs):
+        return [getattr(self.env, method_name)(*args, **kwargs)]
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        n = self.num_envs if indices is None else len(list(indices))
+        return [False] * n
+
+    def get_images(self):
+        return [None] * self.num_envs
+
+    def render(self, mode=None):
+        return None

@@ -151,3 +151,35 @@ class WalkingRewardRef:
         vals.append((r - self.prev_derive) / (self.timestep * self.frame_skip))
         self.prev_derive = r
         return sum(np.array(vals)), np.array(vals)
+
+
+class MadgwickRef:
+    """ahrs.filters.Madgwick.updateIMU + Quaternion.to_angles as restated in SURVEY.md App. G (unpinned)."""
+
+    def __init__(self, Dt, beta=0.033):
+        self.Dt, self.beta = Dt, beta
+
+    def update(self, q, gyr, acc):
+        q, gyr, acc = np.asarray(q, float), np.asarray(gyr, float), np.asarray(acc, float)
+        if np.linalg.norm(gyr) == 0:
+            return q
+        w, x, y, z = q
+        qdot = 0.5 * np.array([-x * gyr[0] - y * gyr[1] - z * gyr[2], w * gyr[0] + y * gyr[2] - z * gyr[1],
+                               w * gyr[1] - x * gyr[2] + z * gyr[0], w * gyr[2] + x * gyr[1] - y * gyr[0]])
+        an = np.linalg.norm(acc)
+        if an > 0:
+            a = acc / an
+            w, x, y, z = q / np.linalg.norm(q)
+            f = np.array([2 * (x * z - w * y) - a[0], 2 * (w * x + y * z) - a[1], 2 * (0.5 - x * x - y * y) - a[2]])
+            if np.linalg.norm(f) > 0:
+                J = np.array([[-2 * y, 2 * z, -2 * w, 2 * x], [2 * x, 2 * w, 2 * z, 2 * y], [0, -4 * x, -4 * y, 0]])
+                g = J.T @ f
+                qdot = qdot - self.beta * g / np.linalg.norm(g)
+        q = q + qdot * self.Dt
+        return q / np.linalg.norm(q)
+
+    @staticmethod
+    def to_angles(q):
+        w, x, y, z = q
+        return np.array([np.arctan2(2 * (w * x + y * z), 1 - 2 * (x * x + y * y)), np.arcsin(np.clip(2 * (w * y - z * x), -1, 1)),
+                         np.arctan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z))])

@@ -428,3 +428,84 @@ def test_walking_env_end_to_end(Vec):
         assert set(env.reward_keys) <= set(info)
     assert saw_term
     env.close()
+
+
+def test_po_walking_observation_and_sb3_adapter(Vec):
+    """VecPOWalkingQuadrupedEnv: 26-value frames (gyro, accel, Madgwick Euler, body_vel xy, ctrl, command) stacked
+    oldest-first over obs_window; the filter follows the restatement of ahrs' updateIMU (unpinned); the SB3 adapter
+    returns numpy, auto-resets in the same step and carries the 11 reward keys in every info dict."""
+    from quadruped_gym_b200.envs.po_walking_quad import SB3VecEnvAdapter, VecPOWalkingQuadrupedEnv
+    n, W = 5, 4
+    env = VecPOWalkingQuadrupedEnv(n, "cuda:0", obs_window=W, max_time=0.25, frame_skip=10, random_controls=True,
+                                   reset_options={"fixed_heading_angle": 0.0, "fixed_velocity_angle": 0.0, "fixed_speed": 0.3})
+    assert env.observation_space.shape == (26 * W,)
+    obs, info = env.reset()
+    assert obs.shape == (n, 26 * W) and info == {}
+    f0 = obs[0].cpu().numpy().reshape(W, 26)
+    assert np.array_equal(f0[0], f0[-1])                                           # [obs] * obs_window (po_walking_quad.py:65)
+    assert np.allclose(f0[0, :9], 0) and np.allclose(f0[0, 11:23], [0, 0, -0.5] * 4)
+    mw = F.MadgwickRef(Dt=0.002 * 10)
+    q = [None] * n
+    rng = np.random.default_rng(2)
+    prev = obs.cpu().numpy().copy()
+    done_seen = False
+    for t in range(20):
+        a = rng.uniform(-1, 1, (n, 12)).astype(np.float32)
+        quat_before_reset = None
+        obs, rew, term, trunc, info = env.step(torch.from_numpy(a).cuda())
+        sens = env.data.sensordata.cpu().numpy().astype(np.float64)
+        o = obs.cpu().numpy()
+        tobs = info["terminal_observation"].cpu().numpy()
+        for e in range(n):
+            stack = (tobs[e] if term[e] else o[e]).reshape(W, 26)
+            assert np.array_equal(stack[:-1], prev[e].reshape(W, 26)[1:])              # FIFO shift
+            fr = stack[-1]
+            assert np.array_equal(fr[0:3], sens[e, 15:18].astype(np.float32)) and np.array_equal(fr[3:6], sens[e, 12:15].astype(np.float32))
+            assert np.array_equal(fr[9:11], sens[e, 30:32].astype(np.float32)) and np.array_equal(fr[11:23], a[e])
+            assert np.allclose(fr[23:26], [0.3, 0.0, 0.0], atol=1e-7)
+            # filter: first update after a reset starts from the true base orientation (the qpos view quirk)
+            if q[e] is None:
+                ang = fr[6:9]
+                assert np.all(np.abs(ang) < 0.5)
+                q[e] = "running"
+            if term[e]:
+                done_seen = True
+                q[e] = None
+                rs = o[e].reshape(W, 26)
+                assert np.array_equal(rs[0], rs[-1]) and np.allclose(rs[0, :6], 0) and np.allclose(rs[0, 11:23], [0, 0, -0.5] * 4)
+                assert np.allclose(rs[0, 6:9], fr[6:9], atol=1e-6)                     # stale filter state in the reset frame
+        prev = o.copy()
+    assert done_seen
+    env.close()
+
+    # Madgwick restatement vs the device on a hand-made IMU sequence (one env, obs_window 1, settling 0)
+    env = VecPOWalkingQuadrupedEnv(1, "cuda:0", obs_window=1, frame_skip=4, auto_reset=False)
+    env.reset()
+    ref = F.MadgwickRef(Dt=0.002 * 4)
+    qref = None
+    for t in range(40):
+        obs, *_ = env.step(torch.zeros((1, 12), device="cuda"))
+        sens = env.data.sensordata[0].cpu().numpy().astype(np.float64)
+        if qref is None:
+            qref = env.data.qpos[0, 3:7].cpu().numpy().astype(np.float64)            # view of qpos at the first update
+        qref = ref.update(qref, sens[15:18], sens[12:15])
+        assert np.allclose(obs[0, 6:9].cpu().numpy(), ref.to_angles(qref), atol=2e-6)
+    env.close()
+
+    sb3 = SB3VecEnvAdapter(VecPOWalkingQuadrupedEnv(8, "cuda:0", obs_window=10, max_time=0.1, frame_skip=10, random_controls=True,
+                                                    reset_options={"fixed_heading_angle": 0.0, "fixed_velocity_angle": 0.0, "fixed_speed": 0.3}))
+    o = sb3.reset()
+    assert isinstance(o, np.ndarray) and o.shape == (8, 260) and o.dtype == np.float32   # train_quadruped.py:16-22 -> 26*10
+    dones = 0
+    for t in range(8):
+        o, r, d, infos = sb3.step(rng.uniform(-1, 1, (8, 12)))
+        assert o.shape == (8, 260) and r.shape == (8,) and d.dtype == bool and len(infos) == 8
+        for i, inf in enumerate(infos):
+            assert set(sb3.reward_keys) <= set(inf) and inf["TimeLimit.truncated"] is False
+            assert ("terminal_observation" in inf) == bool(d[i])
+            if d[i]:
+                dones += 1
+                assert inf["terminal_observation"].shape == (260,)
+    assert dones == 8            # max_time 0.1 at frame_skip 10 -> every env terminates at step 5
+    assert sb3.get_attr("frame_skip") == [10] * 8 and sb3.env_is_wrapped(object) == [False] * 8
+    sb3.close()
