@@ -36,7 +36,7 @@ WORKLOADS = {
     "c2": (4096, 4, 10.0, "C2: batched QuadrupedEnv 4,096 envs, random actions, frame_skip 4"),
     "c3": (65536, 4, 10.0, "C3: 65,536 envs/GPU random-action rollout, frame_skip 4, auto-reset on fall/time-limit"),
     "c4": (8192, 10, 20.0, "C4: PPO rollout collection 8,192 envs x 24-step horizon, frame_skip 10, forward+control+alive rewards"),
-    "c5": (262144, 4, 10.0, "C5: contact-heavy stress 262,144 envs/GPU (pyramidal cone; elliptic not yet implemented)"),
+    "c5": (262144, 4, 10.0, "C5: contact-heavy stress 262,144 envs/GPU, randomised initial poses, actuator kp x5, elliptic friction cone"),
 }
 
 
@@ -180,10 +180,35 @@ def run_ours(a):
     if a.envs:
         envs = a.envs
     rewards = {"forward": R.forward_velocity(1.0), "control_cost": R.ctrl_sq(-0.1), "alive_bonus": R.alive_bonus(1.0)}
+    model_blob, random_init = None, False
+    if a.workload == "c5":   # stress variant of the model: elliptic cone, position-servo gain x5
+        from quadruped_gym_b200.model import DEFAULT_BLOB, blob as qblob
+        A = qblob.unpack(open(DEFAULT_BLOB, "rb").read())
+        A["opt_i"][1] = 1
+        A["act_gain"] = A["act_gain"] * 5.0
+        A["act_bias"] = A["act_bias"].reshape(-1, 3) * np.array([1.0, 5.0, 1.0])
+        model_blob, random_init = qblob.pack(A), True
     env = VecQuadrupedEnv(envs, dev, max_time=max_time, frame_skip=fs, reward_fns=rewards,
                           termination_fns={"flip": R.flip_termination()}, use_default_termination=True,
-                          auto_reset=True, seed=0, env_offset=rank * envs)
+                          auto_reset=True, seed=0, env_offset=rank * envs, model_blob=model_blob, random_init=random_init)
     env.reset()
+    if a.workload == "c5":   # randomised initial poses: yaw U(0,2pi), tilt <= 30 deg, height U(0.05,0.2), joints U(range)
+        g0 = torch.Generator(device=dev)
+        g0.manual_seed(99 + rank)
+        u = lambda *shape: torch.rand(shape, device=dev, generator=g0)
+        q = env.data.qpos
+        yaw, tilt, tdir = u(envs) * 2 * np.pi, u(envs) * np.pi / 6, u(envs) * 2 * np.pi
+        ax = torch.stack([torch.cos(tdir), torch.sin(tdir), torch.zeros_like(tdir)], 1) * torch.sin(tilt / 2)[:, None]
+        qt = torch.cat([torch.cos(tilt / 2)[:, None], ax], 1)
+        qy = torch.stack([torch.cos(yaw / 2), torch.zeros_like(yaw), torch.zeros_like(yaw), torch.sin(yaw / 2)], 1)
+        w1, x1, y1, z1 = qy.unbind(1); w2, x2, y2, z2 = qt.unbind(1)
+        q[:, 3:7] = torch.stack([w1*w2 - x1*x2 - y1*y2 - z1*z2, w1*x2 + x1*w2 + y1*z2 - z1*y2,
+                                 w1*y2 - x1*z2 + y1*w2 + z1*x2, w1*z2 + x1*y2 - y1*x2 + z1*w2], 1)
+        q[:, 2] = 0.05 + 0.15 * u(envs)
+        lo = torch.tensor(np.tile(np.deg2rad([-45, -45, -90]), 4), device=dev, dtype=torch.float32)
+        hi = torch.tensor(np.tile(np.deg2rad([45, 120, 90]), 4), device=dev, dtype=torch.float32)
+        q[:, 7:] = lo + (hi - lo) * u(envs, 12)
+        env.set_state(qpos=q)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
     pool = [torch.rand((envs, 12), device=dev, generator=gen) * 2 - 1 for _ in range(8)]  # resident in HBM

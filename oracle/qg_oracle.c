@@ -554,6 +554,20 @@ static void make_constraint(const qgo_model* m, qgo_data* d) {
         const double* Jt[2] = {jp + nv, jp};
         double sgn[2] = {1, -1};
         double tran = m->body_invweight0[2 * b];
+        if (m->opt_i[1] == 1) {
+            /* elliptic cone: rows normal, t1, t2; friction rows carry pos = margin = 0 (mj_instantiateContact) */
+            for (int k = 0; k < 3 && ne < QGO_MAXEFC; k++) {
+                double* J = d->efc_J + (size_t)ne * nv;
+                for (int i = 0; i < nv; i++) J[i] = k == 0 ? Jn[i] : sgn[k - 1] * Jt[k - 1][i];
+                d->efc_pos[ne] = k == 0 ? d->con_dist[c] : 0.0;
+                d->efc_margin[ne] = k == 0 ? m->geom_margin[g] : 0.0;
+                d->efc_diagApprox[ne] = tran;
+                d->efc_type[ne] = 10 + k; /* 10: normal row of an elliptic contact */
+                d->efc_id[ne] = c;
+                ne++;
+            }
+            continue;
+        }
         for (int k = 0; k < 2; k++)
             for (int s = 0; s < 2 && ne < QGO_MAXEFC; s++) {
                 double* J = d->efc_J + (size_t)ne * nv;
@@ -585,7 +599,40 @@ static void make_constraint(const qgo_model* m, qgo_data* d) {
             double Rpy = 2 * mu * mu * d->efc_R[i];
             for (int k = 0; k < 4; k++) d->efc_R[i + k] = Rpy;
         }
+    for (int i = 0; i < ne; i++)
+        if (d->efc_type[i] == 10) { /* elliptic: friction R = R_normal / impratio (equal sliding coefficients) */
+            double impratio = fmax(MINVAL, m->opt_f[6]);
+            d->efc_R[i + 1] = d->efc_R[i + 2] = d->efc_R[i] / impratio;
+        }
     for (int i = 0; i < ne; i++) d->efc_D[i] = 1.0 / d->efc_R[i];
+}
+
+/* elliptic cone of one contact (rows i, i+1, i+2): zone 0 = satisfied, 1 = fully quadratic, 2 = cone surface.
+   Restates the three-zone cost of MuJoCo's primal solvers in the scaled coordinates U = (mu*jar_n, fri*jar_t). */
+typedef struct { int zone; double cost, f[3], N, T, U1, U2, Dm, mu, fri; } ellzone;
+static ellzone ell_eval(const qgo_model* m, const qgo_data* d, int i, double j0, double j1, double j2) {
+    ellzone z;
+    int g = d->con_geom[d->efc_id[i]];
+    z.fri = m->geom_mu[g];
+    z.mu = z.fri * sqrt(d->efc_R[i + 1] / d->efc_R[i]);
+    z.N = j0 * z.mu; z.U1 = j1 * z.fri; z.U2 = j2 * z.fri;
+    z.T = sqrt(z.U1 * z.U1 + z.U2 * z.U2);
+    z.Dm = d->efc_D[i] / fmax(z.mu * z.mu * (1 + z.mu * z.mu), MINVAL);
+    z.cost = 0; z.f[0] = z.f[1] = z.f[2] = 0;
+    if (z.N >= z.mu * z.T || (z.T <= 0 && z.N >= 0)) z.zone = 0;
+    else if (z.mu * z.N + z.T <= 0 || (z.T <= 0 && z.N < 0)) {
+        z.zone = 1;
+        z.cost = 0.5 * (d->efc_D[i] * j0 * j0 + d->efc_D[i + 1] * j1 * j1 + d->efc_D[i + 2] * j2 * j2);
+        z.f[0] = -d->efc_D[i] * j0; z.f[1] = -d->efc_D[i + 1] * j1; z.f[2] = -d->efc_D[i + 2] * j2;
+    } else {
+        double NmT = z.N - z.mu * z.T;
+        z.zone = 2;
+        z.cost = 0.5 * z.Dm * NmT * NmT;
+        z.f[0] = -z.Dm * NmT * z.mu;
+        z.f[1] = -z.f[0] / z.T * z.U1 * z.fri;
+        z.f[2] = -z.f[0] / z.T * z.U2 * z.fri;
+    }
+    return z;
 }
 
 /* ------------------------------------------------------------------ velocity stage */
@@ -672,9 +719,18 @@ static void actuation(const qgo_model* m, qgo_data* d) {
 
 /* ------------------------------------------------------------------ constraint solver (primal Newton) */
 
+static const qgo_model* g_model_for_cone; /* set by fwd_constraint: the cone helpers need geom_mu */
+
 static double constraint_update(const qgo_data* d, const double* jar, double* force, int* active) {
     double cost = 0;
     for (int i = 0; i < d->nefc; i++) {
+        if (d->efc_type[i] == 10) {
+            ellzone z = ell_eval(g_model_for_cone, d, i, jar[i], jar[i + 1], jar[i + 2]);
+            for (int k = 0; k < 3; k++) { force[i + k] = z.f[k]; active[i + k] = z.zone; }
+            cost += z.cost;
+            i += 2;
+            continue;
+        }
         if (jar[i] < 0) {
             force[i] = -d->efc_D[i] * jar[i];
             active[i] = 1;
@@ -689,6 +745,26 @@ typedef struct { double alpha, cost, d1, d2; } lspoint;
 static lspoint ls_eval(const qgo_data* d, const double* jar, const double* jv, const double* quadG, double a) {
     lspoint p = {a, quadG[0] + a * quadG[1] + a * a * quadG[2], quadG[1] + 2 * a * quadG[2], 2 * quadG[2]};
     for (int i = 0; i < d->nefc; i++) {
+        if (d->efc_type[i] == 10) {
+            double x0 = jar[i] + a * jv[i], x1 = jar[i + 1] + a * jv[i + 1], x2 = jar[i + 2] + a * jv[i + 2];
+            ellzone z = ell_eval(g_model_for_cone, d, i, x0, x1, x2);
+            if (z.zone == 1) {
+                for (int k = 0; k < 3; k++) {
+                    double xk = jar[i + k] + a * jv[i + k];
+                    p.d1 += d->efc_D[i + k] * jv[i + k] * xk;
+                    p.d2 += d->efc_D[i + k] * jv[i + k] * jv[i + k];
+                }
+            } else if (z.zone == 2) {
+                double Np = jv[i] * z.mu, V1 = jv[i + 1] * z.fri, V2 = jv[i + 2] * z.fri;
+                double Tp = (z.U1 * V1 + z.U2 * V2) / z.T, Tpp = (V1 * V1 + V2 * V2 - Tp * Tp) / z.T;
+                double e = z.N - z.mu * z.T, ep = Np - z.mu * Tp;
+                p.d1 += z.Dm * e * ep;
+                p.d2 += z.Dm * (ep * ep - e * z.mu * Tpp);
+            }
+            p.cost += z.cost;
+            i += 2;
+            continue;
+        }
         double x = jar[i] + a * jv[i];
         if (x < 0) {
             p.cost += 0.5 * d->efc_D[i] * x * x;
@@ -759,7 +835,39 @@ static void solve_newton(const qgo_model* m, qgo_data* d) {
             if (improvement < tol || gradient < tol || iter >= m->opt_i[2]) break;
         }
         memcpy(H, d->M, sizeof(double) * nv * nv);
-        for (int r = 0; r < ne; r++)
+        for (int r = 0; r < ne; r++) {
+            if (d->efc_type[r] == 10) {
+                /* 3x3 block W of the contact in jar coordinates, H += J_c^T W J_c */
+                double W[9] = {0};
+                if (active[r] == 1) { W[0] = d->efc_D[r]; W[4] = d->efc_D[r + 1]; W[8] = d->efc_D[r + 2]; }
+                else if (active[r] == 2) {
+                    ellzone z = ell_eval(m, d, r, jar[r], jar[r + 1], jar[r + 2]);
+                    double S[3] = {z.mu, z.fri, z.fri}, U[3] = {z.N, z.U1, z.U2}, e = z.N - z.mu * z.T, Hs[9];
+                    Hs[0] = z.Dm;
+                    for (int j = 1; j < 3; j++) Hs[j] = Hs[3 * j] = -z.Dm * z.mu * U[j] / z.T;
+                    for (int j = 1; j < 3; j++)
+                        for (int k = 1; k < 3; k++)
+                            Hs[3 * j + k] = z.Dm * z.mu * z.mu * U[j] * U[k] / (z.T * z.T) -
+                                            z.Dm * e * z.mu * ((j == k ? 1.0 : 0.0) / z.T - U[j] * U[k] / (z.T * z.T * z.T));
+                    for (int j = 0; j < 3; j++)
+                        for (int k = 0; k < 3; k++) W[3 * j + k] = S[j] * Hs[3 * j + k] * S[k];
+                }
+                if (active[r]) {
+                    const double* Jc = d->efc_J + (size_t)r * nv;
+                    for (int a = 0; a < 3; a++)
+                        for (int bb = 0; bb < 3; bb++) {
+                            double w = W[3 * a + bb];
+                            if (w == 0) continue;
+                            for (int i = 0; i < nv; i++) {
+                                double wi = w * Jc[a * nv + i];
+                                if (wi == 0) continue;
+                                for (int k = 0; k <= i; k++) H[i * nv + k] += wi * Jc[bb * nv + k];
+                            }
+                        }
+                }
+                r += 2;
+                continue;
+            }
             if (active[r]) {
                 const double* J = d->efc_J + (size_t)r * nv;
                 for (int i = 0; i < nv; i++) {
@@ -768,6 +876,7 @@ static void solve_newton(const qgo_model* m, qgo_data* d) {
                     for (int k = 0; k <= i; k++) H[i * nv + k] += w * J[k];
                 }
             }
+        }
         chol_factor(H, nv, nv);
         for (int i = 0; i < nv; i++) search[i] = -grad[i];
         chol_solve(H, nv, nv, search);
@@ -793,6 +902,7 @@ static void solve_newton(const qgo_model* m, qgo_data* d) {
 
 static void fwd_constraint(const qgo_model* m, qgo_data* d) {
     int nv = m->nv, ne = d->nefc;
+    g_model_for_cone = m;
     d->ls_evals = 0;
     if (ne == 0) {
         memcpy(d->qacc, d->qacc_smooth, sizeof(double) * nv);

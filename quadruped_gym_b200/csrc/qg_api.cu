@@ -49,7 +49,7 @@ struct qg_batch {
     QgCounters* d_ctr;
     QgStepOpts opts;
     size_t smem;
-    int num_sms;
+    int num_sms, cone;
     // pinned + device staging for the host-buffer path
     float *h_act, *h_obs, *h_rew, *d_act, *d_obs, *d_rew;
     unsigned char *h_term, *d_term;
@@ -197,8 +197,12 @@ extern "C" int qg_model_load(const void* blob, size_t nbytes, qg_model** out) {
     c.tol = (float)std::fmax(of[4], 1e-6);  // fp32 floor on the solver tolerance ("precision")
     c.scale = (float)(1.0 / (of[8] * (nv > 1 ? nv : 1)));
     c.integrator = oi[0];
-    if (oi[1] != 0) { delete m; return fail(QG_EMODEL, "elliptic friction cones are not implemented yet (cone=pyramidal only)"); }
-    if (of[6] != 1.0) { delete m; return fail(QG_EMODEL, "impratio != 1 is not supported"); }
+    if (oi[1] != 0 && oi[1] != 1) { delete m; return fail(QG_EMODEL, "unknown friction cone type %d", oi[1]); }
+    if (oi[1] == 0 && of[6] != 1.0) { delete m; return fail(QG_EMODEL, "impratio != 1 is supported for elliptic cones only"); }
+    if (!(of[6] > 0)) { delete m; return fail(QG_EMODEL, "impratio must be positive"); }
+    c.cone = oi[1];
+    c.impratio = (float)of[6];
+    c.mu_scale = (float)(1.0 / std::sqrt(of[6]));
     c.max_iter = oi[2] < 20 ? oi[2] : 20;
     c.ls_iter = oi[3] < 12 ? oi[3] : 12;
     c.rule_first = oi[4];
@@ -407,7 +411,8 @@ extern "C" int qg_model_load(const void* blob, size_t nbytes, qg_model** out) {
                 G.B = (float)(2.0 / std::fmax(1e-15, dmax * tc));
                 G.d0 = (float)si[0]; G.dmax = (float)si[1]; G.width = (float)si[2]; G.mid = (float)si[3]; G.power = (float)si[4];
                 double tran = F("body_invweight0")[2 * b];
-                G.Rfac = (float)(2.0 * mu * mu * (1.0 + mu * mu) * tran);
+                // regulariser per unit (1-imp)/imp: pyramidal rows share 2 mu^2 (1+mu^2) tran, the elliptic normal row has tran
+                G.Rfac = (float)(oi[1] == 1 ? tran : 2.0 * mu * mu * (1.0 + mu * mu) * tran);
                 double rb = F("geom_rbound")[g];
                 G.tol2 = (float)(0.09 * rb * rb);
                 G.vert0 = v0; G.nvert = vn;
@@ -492,8 +497,11 @@ extern "C" int qg_batch_create(const qg_model* m, int n_envs, int device, qg_bat
     CUDA_OK(cudaMemset(b->d_state, 0, sizeof(float4) * (size_t)QG_NPLANE * n_envs));
     CUDA_OK(cudaMemset(b->d_ctr, 0, sizeof(QgCounters)));
     b->smem = ((sizeof(QgModelC) + 15) & ~size_t(15)) + sizeof(float4) * nv + sizeof(float) * QG_QR_SLOTS * 32 * (QG_BLOCK / 32);
-    CUDA_OK(cudaFuncSetAttribute(qg_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
-    CUDA_OK(cudaFuncSetAttribute(qg_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+    CUDA_OK(cudaFuncSetAttribute(qg_step_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+    CUDA_OK(cudaFuncSetAttribute(qg_step_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+    CUDA_OK(cudaFuncSetAttribute(qg_step_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+    CUDA_OK(cudaFuncSetAttribute(qg_step_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+    b->cone = m->c.cone;
     *out = b;
     int rc = qg_reset(b, nullptr, 0, 0, 0, nullptr);
     if (rc) return rc;
@@ -570,7 +578,8 @@ template <bool DEBUG>
 static int launch_step(qg_batch* b, const float* action, int clip, int frame_skip, float* obs, float* reward, float* terms,
                        unsigned char* terminated, float* terminal_obs, QgDebugOut dbg, cudaStream_t st) {
     const int blk = step_block(b);
-    qg_step_kernel<DEBUG><<<(4 * b->n + blk - 1) / blk, blk, b->smem, st>>>(b->d_model, b->d_verts, b->d_vert_adj, b->d_adj4, b->d_vert_cadj, b->d_cadj4,
+    auto kern = b->cone ? qg_step_kernel<DEBUG, 1> : qg_step_kernel<DEBUG, 0>;
+    kern<<<(4 * b->n + blk - 1) / blk, blk, b->smem, st>>>(b->d_model, b->d_verts, b->d_vert_adj, b->d_adj4, b->d_vert_cadj, b->d_cadj4,
                                                                      b->d_state, b->n, action, clip, frame_skip, obs, reward,
                                                                      terms, terminated, terminal_obs, b->opts, b->d_ctr, dbg);
     g_launches++;

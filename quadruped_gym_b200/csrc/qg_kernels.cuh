@@ -129,7 +129,7 @@ DI double np_sum12(const double* v) {
     return r;
 }
 
-template <bool DEBUG>
+template <bool DEBUG, int CONE>
 __global__ void __launch_bounds__(QG_BLOCK, QG_MINBLOCKS)
 qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gverts, const int* __restrict__ vert_adj,
                const int4* __restrict__ adj4, const int* __restrict__ vert_cadj, const int4* __restrict__ cadj4, float4* __restrict__ S, int N, const float* __restrict__ action,
@@ -194,7 +194,7 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
                 L.ctrl[0] = c0; L.ctrl[1] = c1; L.ctrl[2] = c2;
                 diverged += (leg == 0);
             }
-            physics_step<DEBUG>(P, sverts, vert_adj, adj4, vert_cadj, cadj4, L, leg, qr, max_iter, ls_iter, s == frame_skip - 1, so,
+            physics_step<DEBUG, CONE>(P, sverts, vert_adj, adj4, vert_cadj, cadj4, L, leg, qr, max_iter, ls_iter, s == frame_skip - 1, so,
                                 st, C, dbg, env);
         }
 

@@ -73,6 +73,8 @@ struct alignas(16) QgModelC {
     float base_damp[6], base_arm[6];
     float tol, scale;  // solver tolerance, 1/(meaninertia*nv)
     int max_iter, ls_iter, rule_first, integrator;
+    int cone;                  // 0 pyramidal, 1 elliptic
+    float impratio, mu_scale;  // elliptic: friction-row D = impratio * D_normal, regularised mu = fri * mu_scale (= 1/sqrt(impratio))
     float lim_K, lim_B, lim_d0, lim_dmax, lim_width, lim_mid, lim_power;
     float qpos0[19];
     QgJointC joint[QG_NLEG][QG_NLINK];

@@ -191,6 +191,56 @@ DI void pyramid_rows(v3 u, v3 tx, v3 ty, v3 up, float mu, float* r) {
     r[0] = un + u1; r[1] = un - u1; r[2] = un + u2; r[3] = un - u2;
 }
 
+// rows of one contact for a point velocity u: pyramidal (4 rows, see pyramid_rows) or elliptic (normal, t1 = +y, t2 = -x)
+template <int CONE>
+DI void contact_rows(v3 u, v3 tx, v3 ty, v3 up, float mu, float* r) {
+    if (CONE) { r[0] = dot(up, u); r[1] = dot(ty, u); r[2] = -dot(tx, u); r[3] = 0.f; }
+    else pyramid_rows(u, tx, ty, up, mu, r);
+}
+
+// Elliptic friction cone of one contact in the scaled coordinates U = (mu*jar_n, fri*jar_t1, fri*jar_t2):
+// zone 0 = inside the cone (no force), 1 = polar cone (all three rows quadratic), 2 = cone surface
+// (cost 1/2 Dm (N - mu T)^2).  mu = fri / sqrt(impratio) is the regularised friction coefficient.
+struct EllZ { int zone; float cost, f0, f1, f2, N, T, U1, U2, Dm, mu; };
+DI EllZ ell_eval(float j0, float j1, float j2, float fri, float mus, float Dn, float Dt) {
+    EllZ z;
+    z.mu = fri * mus;
+    z.N = j0 * z.mu; z.U1 = j1 * fri; z.U2 = j2 * fri;
+    z.T = sqrtf(z.U1 * z.U1 + z.U2 * z.U2);
+    z.Dm = Dn / fmaxf(z.mu * z.mu * (1.f + z.mu * z.mu), 1e-15f);
+    z.cost = 0.f; z.f0 = z.f1 = z.f2 = 0.f;
+    if (z.N >= z.mu * z.T || (z.T <= 0.f && z.N >= 0.f)) z.zone = 0;
+    else if (z.mu * z.N + z.T <= 0.f || (z.T <= 0.f && z.N < 0.f)) {
+        z.zone = 1;
+        z.cost = 0.5f * (Dn * j0 * j0 + Dt * (j1 * j1 + j2 * j2));
+        z.f0 = -Dn * j0; z.f1 = -Dt * j1; z.f2 = -Dt * j2;
+    } else {
+        float NmT = z.N - z.mu * z.T;
+        z.zone = 2;
+        z.cost = 0.5f * z.Dm * NmT * NmT;
+        z.f0 = -z.Dm * NmT * z.mu;
+        float s = -z.f0 / z.T * fri;
+        z.f1 = s * z.U1; z.f2 = s * z.U2;
+    }
+    return z;
+}
+// first and second derivative along jar + alpha*jv, evaluated at x = jar + alpha*jv; returns the zone at x
+DI int ell_ls_acc(float x0, float x1, float x2, float v0, float v1, float v2, float fri, float mus, float Dn, float Dt,
+                  float& e1, float& e2) {
+    EllZ z = ell_eval(x0, x1, x2, fri, mus, Dn, Dt);
+    if (z.zone == 1) {
+        e1 += Dn * v0 * x0 + Dt * (v1 * x1 + v2 * x2);
+        e2 += Dn * v0 * v0 + Dt * (v1 * v1 + v2 * v2);
+    } else if (z.zone == 2) {
+        float Np = v0 * z.mu, V1 = v1 * fri, V2 = v2 * fri;
+        float Tp = (z.U1 * V1 + z.U2 * V2) / z.T, Tpp = (V1 * V1 + V2 * V2 - Tp * Tp) / z.T;
+        float e = z.N - z.mu * z.T, ep = Np - z.mu * Tp;
+        e1 += z.Dm * e * ep;
+        e2 += z.Dm * (ep * ep - e * z.mu * Tpp);
+    }
+    return z.zone;
+}
+
 __device__ __noinline__ float2 sincos_ni(float x) {
     float s, c;
     sincosf(x, &s, &c);
@@ -337,13 +387,15 @@ DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const 
 }
 
 // ---------------------------------------------------------------------------------------------
-template <bool DEBUG>
+template <bool DEBUG, int CONE>
 DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const int* __restrict__ vert_adj,
                      const int4* __restrict__ adj4, const int* __restrict__ vert_cadj,
                      const int4* __restrict__ cadj4, LaneState& S, int leg, const QuadRed& qr,
                      int max_iter, int ls_iter, bool want_sensors, SensorOut& so, StepStats& st, Contacts& C,
                      const QgDebugOut& dbg, int env) {
     const float h = P.timestep;
+    constexpr int NR = CONE ? 3 : 4;   // rows per contact
+    const float mus = P.mu_scale, impr = P.impratio;
     // ---- base frame
     float qn = 1.f / sqrtf(S.qw * S.qw + S.qx * S.qx + S.qy * S.qy + S.qz * S.qz);
     float w = S.qw * qn, x = S.qx * qn, y = S.qy * qn, z = S.qz * qn;
@@ -554,16 +606,16 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
         v3 xc = V3(C.x[c], C.y[c], C.z[c]);
         int lev = C.lev[c];
         float rv[4];
-        pyramid_rows(sel4(U, lev) + cross(sel4(W, lev), xc), tx, ty, up, C.mu[c], rv);
+        contact_rows<CONE>(sel4(U, lev) + cross(sel4(W, lev), xc), tx, ty, up, C.mu[c], rv);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) C.jar[k][c] = fmaf(C.Bd[c], rv[k], C.Kr[c]);  // = -aref_k
+        for (int k = 0; k < NR; ++k) C.jar[k][c] = fmaf(C.Bd[c], rv[k], (CONE && k > 0) ? 0.f : C.Kr[c]);  // = -aref_k
     }
-    qr_put(qr, 0, (float)(4 * nc + nlim));
+    qr_put(qr, 0, (float)(NR * nc + nlim));
     qr_sync(qr);
     const int nefc = (int)qr_get(qr, 0);
     qr_sync(qr);
     st.ncon += nc;
-    st.nefc += 4 * nc + nlim;
+    st.nefc += NR * nc + nlim;
 
     // ---- phase machine around ONE arrow solve: 0 = unconstrained acceleration (H = M, rhs = qfrc_smooth),
     //      1 = Newton direction (H = M + J^T D J, rhs = -grad), 2 = implicit integration
@@ -580,7 +632,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
 #pragma unroll
     for (int i = 0; i < 3; ++i) { rl[i] = fsl[i]; fcl[i] = 0.f; }
     int phase = 0, iter = 0;
-    float cost_old = 0.f;
+    float cost_old = 0.f, impr_est = 0.f;
     bool done = false;
 #pragma unroll 1
     for (;;) {
@@ -621,16 +673,23 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                     v3 xc = V3(C.x[c], C.y[c], C.z[c]);
                     int lev = C.lev[c];
                     float rw[4], rs[4], D = C.D[c];
-                    pyramid_rows(sel4(U, lev) + cross(sel4(W, lev), xc), tx, ty, up, C.mu[c], rw);
-                    pyramid_rows(sel4(U2, lev) + cross(sel4(W2, lev), xc), tx, ty, up, C.mu[c], rs);
+                    contact_rows<CONE>(sel4(U, lev) + cross(sel4(W, lev), xc), tx, ty, up, C.mu[c], rw);
+                    contact_rows<CONE>(sel4(U2, lev) + cross(sel4(W2, lev), xc), tx, ty, up, C.mu[c], rs);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    for (int k = 0; k < NR; ++k) {
                         float base = C.jar[k][c];
                         float jw = rw[k] + base, js = rs[k] + base;
+                        rw[k] = jw; rs[k] = js;
                         C.jar[k][c] = jw;
                         C.jv[k][c] = js;
-                        cw += (jw < 0.f) ? 0.5f * D * jw * jw : 0.f;
-                        cs += (js < 0.f) ? 0.5f * D * js * js : 0.f;
+                        if (!CONE) {
+                            cw += (jw < 0.f) ? 0.5f * D * jw * jw : 0.f;
+                            cs += (js < 0.f) ? 0.5f * D * js * js : 0.f;
+                        }
+                    }
+                    if (CONE) {
+                        cw += ell_eval(rw[0], rw[1], rw[2], C.mu[c], mus, D, D * impr).cost;
+                        cs += ell_eval(rs[0], rs[1], rs[2], C.mu[c], mus, D, D * impr).cost;
                     }
                 }
                 float ljs[3];
@@ -662,7 +721,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
 #pragma unroll 1
                     for (int c = 0; c < nc; ++c)
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) C.jar[k][c] = C.jv[k][c];
+                        for (int k = 0; k < NR; ++k) C.jar[k][c] = C.jv[k][c];
 #pragma unroll
                     for (int k = 0; k < 3; ++k) ljar[k] = ljs[k];
                 }
@@ -685,14 +744,22 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                 v3 xc = V3(C.x[c], C.y[c], C.z[c]);
                 int lev = C.lev[c];
                 float rv[4], D = C.D[c];
-                pyramid_rows(sel4(U, lev) + cross(sel4(W, lev), xc), tx, ty, up, C.mu[c], rv);
+                contact_rows<CONE>(sel4(U, lev) + cross(sel4(W, lev), xc), tx, ty, up, C.mu[c], rv);
+                if (CONE) {
+                    float a0 = C.jar[0][c], a1 = C.jar[1][c], a2 = C.jar[2][c];
+                    C.jv[0][c] = rv[0]; C.jv[1][c] = rv[1]; C.jv[2][c] = rv[2];
+                    int zo0 = ell_ls_acc(a0, a1, a2, rv[0], rv[1], rv[2], C.mu[c], mus, D, D * impr, z1, z2);
+                    int zo1 = ell_ls_acc(a0 + rv[0], a1 + rv[1], a2 + rv[2], rv[0], rv[1], rv[2], C.mu[c], mus, D, D * impr, e1, e2);
+                    flips += (zo0 != zo1 || zo0 == 2) ? 1 : 0;   // the cone surface is not quadratic: iterate
+                } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float jv = rv[k], j0 = C.jar[k][c], j1 = j0 + jv;
-                    C.jv[k][c] = jv;
-                    if (j0 < 0.f) { z1 = fmaf(D * jv, j0, z1); z2 = fmaf(D * jv, jv, z2); }
-                    if (j1 < 0.f) { e1 = fmaf(D * jv, j1, e1); e2 = fmaf(D * jv, jv, e2); }
-                    flips += ((j0 < 0.f) != (j1 < 0.f)) ? 1 : 0;
+                    for (int k = 0; k < 4; ++k) {
+                        float jv = rv[k], j0 = C.jar[k][c], j1 = j0 + jv;
+                        C.jv[k][c] = jv;
+                        if (j0 < 0.f) { z1 = fmaf(D * jv, j0, z1); z2 = fmaf(D * jv, jv, z2); }
+                        if (j1 < 0.f) { e1 = fmaf(D * jv, j1, e1); e2 = fmaf(D * jv, jv, e2); }
+                        flips += ((j0 < 0.f) != (j1 < 0.f)) ? 1 : 0;
+                    }
                 }
             }
 #pragma unroll
@@ -714,8 +781,8 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
             qr_sync(qr);
             st.nls++;
             float alpha = 1.f;
+            const float d10 = z1s + q1;                                // derivative at 0 (< 0: descent direction)
             if (flips != 0) {
-                float d10 = z1s + q1;                                  // derivative at 0 (< 0: descent direction)
                 float d1 = e1s + q1 + 2.f * q2, d2 = e2s + 2.f * q2;
                 float gtol = 1e-4f * fabsf(d10);
                 float lo = 0.f, hi = -1.f;
@@ -732,10 +799,16 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
 #pragma unroll 1
                         for (int c = 0; c < nc; ++c) {
                             float D = C.D[c];
+                            if (CONE) {
+                                float v0 = C.jv[0][c], v1 = C.jv[1][c], v2 = C.jv[2][c];
+                                ell_ls_acc(fmaf(alpha, v0, C.jar[0][c]), fmaf(alpha, v1, C.jar[1][c]), fmaf(alpha, v2, C.jar[2][c]),
+                                           v0, v1, v2, C.mu[c], mus, D, D * impr, e1, e2);
+                            } else {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                float jv = C.jv[k][c], xx = fmaf(alpha, jv, C.jar[k][c]);
-                                if (xx < 0.f) { e1 = fmaf(D * jv, xx, e1); e2 = fmaf(D * jv, jv, e2); }
+                                for (int k = 0; k < 4; ++k) {
+                                    float jv = C.jv[k][c], xx = fmaf(alpha, jv, C.jar[k][c]);
+                                    if (xx < 0.f) { e1 = fmaf(D * jv, xx, e1); e2 = fmaf(D * jv, jv, e2); }
+                                }
                             }
                         }
 #pragma unroll
@@ -760,9 +833,12 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
 #pragma unroll 1
             for (int c = 0; c < nc; ++c)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) C.jar[k][c] = fmaf(alpha, C.jv[k][c], C.jar[k][c]);
+                for (int k = 0; k < NR; ++k) C.jar[k][c] = fmaf(alpha, C.jv[k][c], C.jar[k][c]);
             iter++;
             if (flips == 0) conv = true;  // the quadratic model was exact along the whole step: this is the optimum
+            // decrease of the cost along the step from the line-search model (-1/2 alpha d1(0) for an exact search on a
+            // quadratic).  In fp32 the difference of two cost values is not resolvable once |cost| * 1e-7 > tolerance.
+            impr_est = -0.5f * alpha * d10;
         }
 
         float gb[6], gl[3];
@@ -774,14 +850,21 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
 #pragma unroll 1
             for (int c = 0; c < nc; ++c) {
                 float D = C.D[c], mu = C.mu[c];
-                float j0 = C.jar[0][c], j1 = C.jar[1][c], j2 = C.jar[2][c], j3 = C.jar[3][c];
-                float f0 = j0 < 0.f ? -D * j0 : 0.f, f1 = j1 < 0.f ? -D * j1 : 0.f;
-                float f2 = j2 < 0.f ? -D * j2 : 0.f, f3 = j3 < 0.f ? -D * j3 : 0.f;
-                cost -= 0.5f * (f0 * j0 + f1 * j1 + f2 * j2 + f3 * j3);
                 v3 xc = V3(C.x[c], C.y[c], C.z[c]);
                 int lev = C.lev[c];
-                // force vector in B: sum f_k w_k,  w = up +- mu*ty, up -+ mu*tx
-                v3 fc = fma3(f0 + f1 + f2 + f3, up, fma3(mu * (f0 - f1), ty, (-mu * (f2 - f3)) * tx));
+                v3 fc;
+                if (CONE) {
+                    EllZ z = ell_eval(C.jar[0][c], C.jar[1][c], C.jar[2][c], mu, mus, D, D * impr);
+                    cost += z.cost;
+                    fc = fma3(z.f0, up, fma3(z.f1, ty, (-z.f2) * tx));   // rows: n = up, t1 = ty, t2 = -tx
+                } else {
+                    float j0 = C.jar[0][c], j1 = C.jar[1][c], j2 = C.jar[2][c], j3 = C.jar[3][c];
+                    float f0 = j0 < 0.f ? -D * j0 : 0.f, f1 = j1 < 0.f ? -D * j1 : 0.f;
+                    float f2 = j2 < 0.f ? -D * j2 : 0.f, f3 = j3 < 0.f ? -D * j3 : 0.f;
+                    cost -= 0.5f * (f0 * j0 + f1 * j1 + f2 * j2 + f3 * j3);
+                    // force vector in B: sum f_k w_k,  w = up +- mu*ty, up -+ mu*tx
+                    fc = fma3(f0 + f1 + f2 + f3, up, fma3(mu * (f0 - f1), ty, (-mu * (f2 - f3)) * tx));
+                }
                 v3 nn = cross(xc, fc);
                 Fb += fc;
                 Nb += nn;
@@ -819,7 +902,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
             for (int r = 0; r < 6; ++r) { gb[r] = Mab[r] - fsb[r] - fcb[r]; g2b += gb[r] * gb[r]; }
             if (phase == 1 && !conv) {
                 float gradient = P.scale * sqrtf(g2 + g2b);
-                float improvement = P.scale * (cost_old - cost);
+                float improvement = P.scale * impr_est;
                 conv = improvement < P.tol || gradient < P.tol || iter >= max_iter;
             }
             cost_old = cost;
@@ -850,23 +933,45 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
 #pragma unroll 1
             for (int c = 0; c < nc; ++c) {
                 float D = C.D[c], mu = C.mu[c];
-                float a0 = C.jar[0][c] < 0.f ? 1.f : 0.f, a1 = C.jar[1][c] < 0.f ? 1.f : 0.f;
-                float a2 = C.jar[2][c] < 0.f ? 1.f : 0.f, a3 = C.jar[3][c] < 0.f ? 1.f : 0.f;
-                float na = a0 + a1 + a2 + a3;
-                if (na == 0.f) continue;
+                // W = 3x3 stiffness of the contact in the basis (e0, e1, e2) = (up, ty, -tx): w00 w11 w22 w01 w02 w12
+                float w00, w11, w22, w01, w02, w12;
+                if (CONE) {
+                    EllZ z = ell_eval(C.jar[0][c], C.jar[1][c], C.jar[2][c], mu, mus, D, D * impr);
+                    if (z.zone == 0) continue;
+                    if (z.zone == 1) { w00 = D; w11 = w22 = D * impr; w01 = w02 = w12 = 0.f; }
+                    else {
+                        float iT = 1.f / z.T, e = z.N - z.mu * z.T;
+                        float a = z.Dm * z.mu * z.mu * iT * iT + z.Dm * e * z.mu * iT * iT * iT;   // coefficient of U_j U_k
+                        float b = -z.Dm * e * z.mu * iT;                                       // coefficient of delta_jk
+                        float sn = z.mu, stt = mu;                                             // dU/djar = diag(mu_reg, fri, fri)
+                        w00 = sn * sn * z.Dm;
+                        w01 = sn * stt * (-z.Dm * z.mu * z.U1 * iT);
+                        w02 = sn * stt * (-z.Dm * z.mu * z.U2 * iT);
+                        w11 = stt * stt * (a * z.U1 * z.U1 + b);
+                        w22 = stt * stt * (a * z.U2 * z.U2 + b);
+                        w12 = stt * stt * (a * z.U1 * z.U2);
+                    }
+                } else {
+                    float a0 = C.jar[0][c] < 0.f ? 1.f : 0.f, a1 = C.jar[1][c] < 0.f ? 1.f : 0.f;
+                    float a2 = C.jar[2][c] < 0.f ? 1.f : 0.f, a3 = C.jar[3][c] < 0.f ? 1.f : 0.f;
+                    float na = a0 + a1 + a2 + a3;
+                    if (na == 0.f) continue;
+                    // rows w0 = e0 + mu e1, w1 = e0 - mu e1, w2 = e0 + mu e2, w3 = e0 - mu e2
+                    w00 = D * na; w11 = D * mu * mu * (a0 + a1); w22 = D * mu * mu * (a2 + a3);
+                    w01 = D * mu * (a0 - a1); w02 = D * mu * (a2 - a3); w12 = 0.f;
+                }
                 v3 xc = V3(C.x[c], C.y[c], C.z[c]);
                 int lev = C.lev[c];
                 // Jacobian columns of the leg joints at the contact point (zero above the contact's link)
                 v3 jc0 = lev >= 1 ? sl[0] + cross(sa[0], xc) : V3(0, 0, 0);
                 v3 jc1 = lev >= 2 ? sl[1] + cross(sa[1], xc) : V3(0, 0, 0);
                 v3 jc2 = lev >= 3 ? sl[2] + cross(sa[2], xc) : V3(0, 0, 0);
-                // W = D * sum_active w w^T in the (tx, ty, up) basis; w0=up+mu ty, w1=up-mu ty, w2=up-mu tx, w3=up+mu tx
-                float sy = a0 + a1, sx = a2 + a3, dy = a0 - a1, dx = a3 - a2;
-                float wuu = D * na, wyy = D * mu * mu * sy, wxx = D * mu * mu * sx, wuy = D * mu * dy, wux = D * mu * dx;
-#define WMUL(v, out)                                                                                   \
-    {                                                                                                  \
-        float pu = dot(up, v), py = dot(ty, v), px = dot(tx, v);                                       \
-        out = fma3(wuu * pu + wuy * py + wux * px, up, fma3(wyy * py + wuy * pu, ty, (wxx * px + wux * pu) * tx)); \
+#define WMUL(v, out)                                                                             \
+    {                                                                                            \
+        float p0 = dot(up, v), p1 = dot(ty, v), p2 = -dot(tx, v);                                \
+        float c0 = w00 * p0 + w01 * p1 + w02 * p2, c1 = w01 * p0 + w11 * p1 + w12 * p2;          \
+        float c2 = w02 * p0 + w12 * p1 + w22 * p2;                                               \
+        out = fma3(c0, up, fma3(c1, ty, (-c2) * tx));                                            \
     }
                 v3 Wx, Wy, Wz, q0, q1v, q2v;
                 WMUL(V3(1, 0, 0), Wx);

@@ -127,7 +127,7 @@ class VecQuadrupedEnv:
                  frame_skip: int = 4, render_mode: Optional[str] = None, reward_fns: Optional[dict] = None,
                  termination_fns: Optional[dict] = None, use_default_termination: bool = True,
                  auto_reset: bool = True, seed: int = 0, env_offset: int = 0, random_init: bool = False,
-                 mesh_inertia: str = "legacy", **unused_render_kwargs):
+                 mesh_inertia: str = "legacy", model_blob: Optional[bytes] = None, **unused_render_kwargs):
         if render_mode is not None:
             raise NotImplementedError("rendering is out of scope for the B200 batched path (render_mode must be None)")
         self.device = torch.device(device)
@@ -136,7 +136,7 @@ class VecQuadrupedEnv:
         L = _lib.lib()
         self.num_envs = int(num_envs)
         self.model_path = model_path
-        blob = load_model_blob(model_path, mesh_inertia)
+        blob = model_blob if model_blob is not None else load_model_blob(model_path, mesh_inertia)
         self._model = C.c_void_p()
         _lib.check(L.qg_model_load(blob, len(blob), C.byref(self._model)), "qg_model_load")
         self.model = ModelView(self._model, blob)

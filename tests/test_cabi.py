@@ -52,9 +52,16 @@ def test_bad_blobs_are_rejected_with_codes(blob):
     raw = qblob.pack(A3)
     assert L.qg_model_load(raw, len(raw), C.byref(h)) == -3 and b"axis" in L.qg_last_error()
     A4 = {k: v.copy() for k, v in A.items()}
-    A4["opt_i"][1] = 1                              # elliptic cone: not implemented yet
+    A4["opt_f"][6] = 2.0                            # impratio != 1 with the pyramidal cone
     raw = qblob.pack(A4)
-    assert L.qg_model_load(raw, len(raw), C.byref(h)) == -3 and b"elliptic" in L.qg_last_error()
+    assert L.qg_model_load(raw, len(raw), C.byref(h)) == -3 and b"impratio" in L.qg_last_error()
+    A4["opt_i"][1] = 1                              # elliptic cone with impratio 2: supported
+    raw = qblob.pack(A4)
+    assert L.qg_model_load(raw, len(raw), C.byref(h)) == 0
+    L.qg_model_destroy(h)
+    A4["opt_i"][1] = 7
+    raw = qblob.pack(A4)
+    assert L.qg_model_load(raw, len(raw), C.byref(h)) == -3 and b"cone" in L.qg_last_error()
     with pytest.raises(ValueError):
         _lib.check(-3, "qg_model_load")
 

@@ -181,3 +181,30 @@ def test_reset_state_and_time_limit_index(oracle_model):
         t += 0.002
         n += 1
     assert n == 10001        # -> env.step() #1001 at frame_skip 10
+
+
+@pytest.mark.parametrize("impratio", [1.0, 4.0])
+def test_elliptic_cone_stand_and_optimality(blob, impratio):
+    """Elliptic friction cone (BASELINE config 5): static stand carries the weight with forces inside the cone,
+    and the solver's point satisfies the first-order optimality of the three-zone cone cost."""
+    A = qblob.unpack(blob)
+    A["opt_i"][1] = 1
+    A["opt_f"][6] = impratio
+    om = OracleModel(qblob.pack(A))
+    d = OracleData(om)
+    d.ctrl[:] = [0, 0, -0.5] * 4
+    for _ in range(1200):
+        d.step()
+    assert d.ncon == 4 and d.nefc == 12
+    f = d.efc_force.reshape(-1, 3)
+    assert f[:, 0].sum() == pytest.approx(1.110 * 9.81, rel=2e-3)
+    assert np.all(np.hypot(f[:, 1], f[:, 2]) <= 1.0 * f[:, 0] + 1e-9)        # |f_t| <= mu f_n, mu = 1
+    r = d.M @ d.qacc - d.qfrc_smooth - d.efc_J.T @ d.efc_force
+    assert np.abs(r).max() < 1e-7
+    rng = np.random.default_rng(3)
+    for t in range(150):                                                       # sliding / stumbling states
+        d.env_step(rng.uniform(-1, 1, 12), 4)
+        if d.nefc:
+            r = d.M @ d.qacc - d.qfrc_smooth - d.efc_J.T @ d.efc_force
+            assert np.abs(r).max() < 1e-5 * max(1.0, np.abs(d.qfrc_smooth).max())
+    assert d.warnings == 0

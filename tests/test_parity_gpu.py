@@ -509,3 +509,49 @@ def test_po_walking_observation_and_sb3_adapter(Vec):
     assert dones == 8            # max_time 0.1 at frame_skip 10 -> every env terminates at step 5
     assert sb3.get_attr("frame_skip") == [10] * 8 and sb3.env_is_wrapped(object) == [False] * 8
     sb3.close()
+
+
+@pytest.mark.parametrize("impratio", [1.0, 4.0])
+def test_elliptic_cone_parity(Vec, blob, impratio):
+    """Elliptic friction cones (BASELINE config 5): teacher-forced single-step parity against the oracle on states
+    from elliptic-cone rollouts (sticking, sliding and separating contacts), same tolerances as the pyramidal test."""
+    from oracle.oracle import OracleModel
+    from quadruped_gym_b200.model import blob as qblob
+    A = qblob.unpack(blob)
+    A["opt_i"][1] = 1
+    A["opt_f"][6] = impratio
+    eb = qblob.pack(A)
+    om = OracleModel(eb)
+    n = 256
+    st = rollout_states(om, n, 150, seed=17)
+    st32 = {k: v.astype(np.float32) for k, v in st.items() if k != "time"}
+    env = Vec(n, "cuda:0", auto_reset=False, model_blob=eb)
+    env.set_state(qpos=st32["qpos"], qvel=st32["qvel"], act=st32["act"], qacc_warmstart=st32["warm"], time=st["time"], ctrl=st32["ctrl"])
+    ctrl = np.random.default_rng(5).uniform(-1, 1, (n, 12)).astype(np.float32)
+    out = {k: v.cpu().numpy() for k, v in env.debug_step(ctrl).items()}
+    gq, gv = env.data.qpos.cpu().numpy(), env.data.qvel.cpu().numpy()
+    same = cone_zone = 0
+    for e in range(n):
+        d = _oracle_at(om, st32, st["time"], ctrl, e)
+        d.forward()
+        if out["counts"][e, 0] != d.ncon:
+            continue
+        same += 1
+        assert out["counts"][e, 1] == d.nefc == 3 * d.ncon + d.nlimit
+        f = d.efc_force[d.nlimit:].reshape(-1, 3)
+        cone_zone += int(np.any((f[:, 0] > 0) & (np.hypot(f[:, 1], f[:, 2]) > 0.999 * f[:, 0])))   # sliding contacts
+        tol = 1e-4 if d.nefc == 0 else 2e-3
+        assert np.abs(out["qacc"][e] - d.qacc).max() <= tol * max(1.0, np.abs(d.qacc).max()), (e, d.ncon, d.solver_niter)
+        d2 = _oracle_at(om, st32, st["time"], ctrl, e)
+        d2.step()
+        assert np.abs(gq[e] - d2.qpos).max() <= 1e-5
+        assert np.abs(gv[e] - d2.qvel).max() <= 2e-4 * max(1.0, np.abs(d2.qvel).max())
+    assert same >= 0.97 * n and cone_zone >= 10
+    # stability over a rollout: no divergence, forces keep the robot up
+    env.reset()
+    a = torch.zeros((n, 12), device="cuda"); a[:, 2::3] = -0.5
+    for _ in range(300):
+        obs, *_ = env.step(a)
+    assert env.counters()["diverged"] == 0
+    assert torch.allclose(obs[:, 20], torch.full((n,), 0.143, device="cuda"), atol=3e-3)   # standing height
+    env.close()
