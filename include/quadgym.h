@@ -122,8 +122,9 @@ int qg_reset(qg_batch* b, const uint8_t* mask_dev, uint64_t seed, int random_yaw
 int qg_step(qg_batch* b, const float* action_dev, int frame_skip, float* obs_dev, float* reward_dev,
             float* terms_dev, uint8_t* terminated_dev, float* terminal_obs_dev, void* stream);
 
-/* Same call with HOST buffers: H2D of the actions, qg_step, D2H of obs / reward / terminated
- * through pinned staging buffers, then a stream synchronise.  This is the end-to-end path. */
+/* Same call with HOST buffers: H2D of the actions, qg_step, D2H of obs / reward / terminated straight from / into
+ * the caller's buffers (page-locked buffers are DMA-ed without staging), then a stream synchronise.
+ * This is the end-to-end path. */
 int qg_step_host(qg_batch* b, const float* action_host, int frame_skip, float* obs_host,
                  float* reward_host, uint8_t* terminated_host, void* stream);
 

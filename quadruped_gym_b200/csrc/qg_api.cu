@@ -605,29 +605,23 @@ extern "C" int qg_step_host(qg_batch* b, const float* action_host, int frame_ski
     CUDA_OK(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = b->n;
-    if (!b->h_act) {
-        CUDA_OK(cudaMallocHost(&b->h_act, n * 12 * sizeof(float)));
-        CUDA_OK(cudaMallocHost(&b->h_obs, n * 33 * sizeof(float)));
-        CUDA_OK(cudaMallocHost(&b->h_rew, n * sizeof(float)));
-        CUDA_OK(cudaMallocHost(&b->h_term, n));
+    if (!b->d_act) {
         CUDA_OK(cudaMalloc(&b->d_act, n * 12 * sizeof(float)));
         CUDA_OK(cudaMalloc(&b->d_obs, n * 33 * sizeof(float)));
         CUDA_OK(cudaMalloc(&b->d_rew, n * sizeof(float)));
         CUDA_OK(cudaMalloc(&b->d_term, n));
     }
-    memcpy(b->h_act, action_host, n * 12 * sizeof(float));
-    CUDA_OK(cudaMemcpyAsync(b->d_act, b->h_act, n * 12 * sizeof(float), cudaMemcpyHostToDevice, st));
+    // the copies run straight from / into the caller's buffers: page-locked buffers (cudaHostAlloc, torch pin_memory)
+    // are DMA-ed asynchronously, pageable ones go through the driver's staging
+    CUDA_OK(cudaMemcpyAsync(b->d_act, action_host, n * 12 * sizeof(float), cudaMemcpyHostToDevice, st));
     QgDebugOut dbg;
     memset(&dbg, 0, sizeof dbg);
     int rc = launch_step<false>(b, b->d_act, 1, frame_skip, b->d_obs, b->d_rew, nullptr, b->d_term, nullptr, dbg, st);
     if (rc) return rc;
-    CUDA_OK(cudaMemcpyAsync(b->h_obs, b->d_obs, n * 33 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(b->h_rew, b->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(b->h_term, b->d_term, n, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(obs_host, b->d_obs, n * 33 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(reward_host, b->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(terminated_host, b->d_term, n, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
-    memcpy(obs_host, b->h_obs, n * 33 * sizeof(float));
-    memcpy(reward_host, b->h_rew, n * sizeof(float));
-    memcpy(terminated_host, b->h_term, n);
     return QG_OK;
 }
 

@@ -345,27 +345,31 @@ DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const 
         m3 RB = matmul(Rk, ldm3(G.R));  // mesh frame -> B
         const int* __restrict__ e = reinterpret_cast<const int*>(el + __ldg(va + best));
         int cnt = 0, cand_v = best;
-        v3 prev0 = V3(0, 0, 0), prev1 = prev0, prev2 = prev0;
+        // heights and mutual distances of the candidates are evaluated in the mesh frame (rigid-motion invariant);
+        // only vertices that become contacts are transformed to the base frame
+        float4 prev0 = make_float4(0.f, 0.f, 0.f, 0.f), prev1 = prev0, prev2 = prev0;
 #pragma unroll 1
         for (;;) {
             float4 v = vt[cand_v];
-            v3 xv = ctr + mul(RB, V3(v.x, v.y, v.z));
-            float dv = zb + dot(up, xv);
+            float dv = zc + fmaf(dl.x, v.x, fmaf(dl.y, v.y, dl.z * v.z));
             bool ok = (cnt == 0) || (dv <= margin);
             if (ok && cnt > 0) {
-                v3 e0 = xv - prev0, e1 = xv - prev1, e2 = xv - prev2;
-                if (dot(e0, e0) < G.tol2) ok = false;
+                float ax = v.x - prev0.x, ay = v.y - prev0.y, az = v.z - prev0.z;
+                if (ax * ax + ay * ay + az * az < G.tol2) ok = false;
                 if (!P.rule_first) {
-                    if (cnt > 1 && dot(e1, e1) < G.tol2) ok = false;
-                    if (cnt > 2 && dot(e2, e2) < G.tol2) ok = false;
+                    float bx = v.x - prev1.x, by = v.y - prev1.y, bz = v.z - prev1.z;
+                    float cx = v.x - prev2.x, cy = v.y - prev2.y, cz = v.z - prev2.z;
+                    if (cnt > 1 && bx * bx + by * by + bz * bz < G.tol2) ok = false;
+                    if (cnt > 2 && cx * cx + cy * cy + cz * cz < G.tol2) ok = false;
                 }
             }
             if (ok) {
-                if (cnt == 0) prev0 = xv; else if (cnt == 1) prev1 = xv; else if (cnt == 2) prev2 = xv;
+                if (cnt == 0) prev0 = v; else if (cnt == 1) prev1 = v; else if (cnt == 2) prev2 = v;
                 cnt++;
                 if (dv < margin) {  // includemargin: rows are instantiated only for dist < margin
                     if (C.n < QG_MAXCON_LANE) {
                         int c = C.n++;
+                        v3 xv = ctr + mul(RB, V3(v.x, v.y, v.z));
                         v3 xc = fma3(-0.5f * dv, up, xv);
                         float r = dv - margin;
                         float imp = impedance(r, G.d0, G.dmax, G.width, G.mid, G.power);

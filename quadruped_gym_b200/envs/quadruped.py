@@ -246,14 +246,23 @@ class VecQuadrupedEnv:
         truncated = torch.zeros_like(terminated)  # quadruped.py:179
         return self._obs, reward, terminated, truncated, info
 
+    def pinned_action_buffer(self) -> np.ndarray:
+        """A page-locked [N,12] float32 array: fill it and pass it to ``step_host`` for a staging-free H2D copy."""
+        if not hasattr(self, "_h_act"):
+            self._h_act_t = torch.empty((self.num_envs, 12), dtype=torch.float32).pin_memory()
+            self._h_act = self._h_act_t.numpy()
+        return self._h_act
+
     def step_host(self, action: np.ndarray):
-        """End-to-end call with HOST buffers (numpy in, numpy out): qg_step_host."""
+        """End-to-end call with HOST buffers (numpy in, numpy out): qg_step_host.  The returned arrays are views of
+        page-locked buffers owned by the env (valid until the next call)."""
         self._sync_tables()
         a = np.ascontiguousarray(action, dtype=np.float32).reshape(self.num_envs, 12)
         if not hasattr(self, "_h_obs"):
-            self._h_obs = np.empty((self.num_envs, 33), dtype=np.float32)
-            self._h_rew = np.empty((self.num_envs,), dtype=np.float32)
-            self._h_term = np.empty((self.num_envs,), dtype=np.uint8)
+            self._h_out = [torch.empty((self.num_envs, 33), dtype=torch.float32).pin_memory(),
+                           torch.empty((self.num_envs,), dtype=torch.float32).pin_memory(),
+                           torch.empty((self.num_envs,), dtype=torch.uint8).pin_memory()]
+            self._h_obs, self._h_rew, self._h_term = (t.numpy() for t in self._h_out)
         _lib.check(_lib.lib().qg_step_host(self._batch, a.ctypes.data_as(C.c_void_p), self.frame_skip,
                                            self._h_obs.ctypes.data_as(C.c_void_p), self._h_rew.ctypes.data_as(C.c_void_p),
                                            self._h_term.ctypes.data_as(C.c_void_p), self._stream()), "qg_step_host")

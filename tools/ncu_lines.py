@@ -2,7 +2,7 @@
 nvdisasm --print-line-info of the kernel in libquadgym.so.  Usage: ncu_lines.py rep.ncu-rep [kernel-substr]"""
 import collections, csv, io, os, re, subprocess, sys, tempfile
 rep = sys.argv[1]
-ksub = sys.argv[2] if len(sys.argv) > 2 else "qg_step_kernelILb0"
+ksub = sys.argv[2] if len(sys.argv) > 2 else "qg_step_kernelILb0ELi0"
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "quadruped_gym_b200", "libquadgym.so")], cwd=tmp, capture_output=True)
