@@ -135,7 +135,8 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
                const int4* __restrict__ adj4, const int* __restrict__ vert_cadj, const int4* __restrict__ cadj4, float4* __restrict__ S, int N, const float* __restrict__ action,
                int clip_action, int frame_skip, float* __restrict__ obs, float* __restrict__ reward,
                float* __restrict__ terms, unsigned char* __restrict__ terminated, float* __restrict__ terminal_obs,
-               QgStepOpts opts, QgCounters* __restrict__ ctr, QgDebugOut dbg) {
+               QgStepOpts opts, QgCounters* __restrict__ ctr, QgDebugOut dbg, const int* __restrict__ perm,
+               unsigned char* __restrict__ bin_key) {
     extern __shared__ __align__(16) unsigned char smem[];
     QgModelC& P = *reinterpret_cast<QgModelC*>(smem);
     float4* sverts = reinterpret_cast<float4*>(smem + ((sizeof(QgModelC) + 15) & ~size_t(15)));
@@ -154,7 +155,10 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
     // quads past the end of the batch shadow the last environment (same reads, no writes) so that every thread
     // of the block reaches the same barriers
     const bool valid = (t >> 2) < N;
-    const int env = valid ? (t >> 2) : N - 1;
+    // `perm` (optional) maps quad slots to environments: environments with similar contact / solver effort in the
+    // previous launch share warps (less SIMT divergence); results per environment do not depend on the slot
+    const int slot = valid ? (t >> 2) : N - 1;
+    const int env = perm ? perm[slot] : slot;
     if (!valid) { dbg.qacc = dbg.qacc_smooth = dbg.qfrc_bias = dbg.M = dbg.sensordata = nullptr; dbg.counts = nullptr; }
     const unsigned qm = 0xFu << (threadIdx.x & 28);
     unsigned long long cv[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -179,6 +183,7 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
 
         StepStats st;
         st.ncon = st.nefc = st.niter = st.nls = st.nvert = st.overflow = 0;
+        st.last_nefc = st.last_iter = 0;
         int diverged = 0;
         SensorOut so;
         Contacts C;
@@ -295,6 +300,10 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
         cv[4] = leg == 0 ? st.nls : 0; cv[5] = st.nvert; cv[6] = diverged; cv[7] = st.overflow;
         cv[8] = (leg == 0 && term) ? 1 : 0;
         }
+        if (bin_key) {   // key of the next launch's binning: which legs were in contact, and the Newton iterations needed
+            int pattern = qsumi((C.n > 0 ? 1 : 0) << leg, qm);
+            if (leg == 0 && valid) bin_key[env] = (unsigned char)(min(st.last_iter, 3) * 16 + pattern);
+        }
     }
 
     // ---- counters: warp shuffle reduce, one atomic per warp and counter
@@ -407,4 +416,35 @@ __global__ void qg_ffma_kernel(float* out, int iters, float a, float b) {
         }
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Counting sort of the environments by the key the step kernel left (64 bins: Newton iterations x which legs were in
+// contact in the last physics step).  Two tiny launches per env.step(); the order inside a bin is irrelevant.
+#define QG_NBINS 64
+__global__ void qg_bin_hist_kernel(const unsigned char* __restrict__ key, int N, int* __restrict__ count) {
+    __shared__ int sc[QG_NBINS];
+    if (threadIdx.x < QG_NBINS) sc[threadIdx.x] = 0;
+    __syncthreads();
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < N; e += gridDim.x * blockDim.x) atomicAdd(&sc[key[e] & (QG_NBINS - 1)], 1);
+    __syncthreads();
+    if (threadIdx.x < QG_NBINS && sc[threadIdx.x]) atomicAdd(&count[threadIdx.x], sc[threadIdx.x]);
+}
+__global__ void qg_bin_scatter_kernel(const unsigned char* __restrict__ key, int N, const int* __restrict__ count,
+                                      int* __restrict__ cursor, int* __restrict__ perm) {
+    __shared__ int base[QG_NBINS], sc[QG_NBINS], sbase[QG_NBINS];
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < QG_NBINS; ++b) { base[b] = acc; acc += count[b]; }
+    }
+    if (threadIdx.x < QG_NBINS) sc[threadIdx.x] = 0;
+    __syncthreads();
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = 0, local = 0;
+    if (e < N) { b = key[e] & (QG_NBINS - 1); local = atomicAdd(&sc[b], 1); }
+    __syncthreads();
+    if (threadIdx.x < QG_NBINS && sc[threadIdx.x]) sbase[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], sc[threadIdx.x]);
+    __syncthreads();
+    if (e < N) perm[base[b] + sbase[b] + local] = e;
 }

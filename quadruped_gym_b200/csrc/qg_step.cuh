@@ -41,6 +41,7 @@ struct SensorOut {
 
 struct StepStats {
     int ncon, nefc, niter, nls, nvert, overflow;
+    int last_nefc, last_iter;   // of the most recent physics step (env totals): the binning key of the next launch
 };
 
 // per-lane contact table (thread-local memory; only the first `nc` slots are ever touched)
@@ -1017,6 +1018,8 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
         }
     }
     st.niter += (leg == 0) ? iter : 0;
+    st.last_nefc = nefc;
+    st.last_iter = iter;
 
     // ---- sensors of this forward pass (pre-integration state, solver qacc)
     if (want_sensors) {
