@@ -577,3 +577,33 @@ def test_env_binning_does_not_change_results(Vec, monkeypatch):
     for a, b in zip(*outs):
         for x, y in zip(a, b):
             assert torch.equal(x, y)
+
+
+def test_full_size_properties_and_rollout_buffer(Vec):
+    """BASELINE sizes (65,536 envs): size-independent properties -- identical environments stay bit-identical under
+    identical actions, every value stays finite, counters add up, and the [T,N,.] rollout buffer of config 4 fills on
+    the device."""
+    from quadruped_gym_b200.envs import rewards as R
+    from quadruped_gym_b200.rollout import RolloutBuffer
+    n = 65536
+    env = Vec(n, "cuda:0", auto_reset=True, termination_fns={"flip": R.flip_termination()},
+              reward_fns={"forward": R.forward_velocity(1.0), "control_cost": R.ctrl_sq(-0.1), "alive_bonus": R.alive_bonus(1.0)})
+    env.reset()
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    for t in range(40):      # all environments receive the same action -> they must remain identical
+        a = (torch.rand((1, 12), device="cuda", generator=g) * 2 - 1).expand(n, 12).contiguous()
+        obs, rew, term, _, _ = env.step(a)
+    assert bool(torch.isfinite(obs).all()) and bool((obs == obs[0]).all()) and bool((rew == rew[0]).all())
+    assert torch.equal(env.data.qpos, env.data.qpos[:1].expand(n, 19))
+    c = env.counters(reset=True)
+    assert c["physics_steps"] == n * 40 * 4 and c["contacts"] % n == 0 and c["diverged"] == 0 and c["contact_overflow"] == 0
+    env.close()
+    env = Vec(8192, "cuda:0", frame_skip=10, max_time=20.0, auto_reset=True, termination_fns={"flip": R.flip_termination()},
+              reward_fns={"forward": R.forward_velocity(1.0), "control_cost": R.ctrl_sq(-0.1), "alive_bonus": R.alive_bonus(1.0)})
+    buf = RolloutBuffer(env, 24).collect(generator=g)
+    assert buf.obs.shape == (25, 8192, 33) and buf.actions.shape == (24, 8192, 12)
+    assert torch.count_nonzero(buf.obs[0]) == 0 and torch.count_nonzero(buf.obs[1]) > 0
+    ref = 1.0 - 0.1 * (buf.actions.double() ** 2).sum(-1)          # alive + control cost part of the fused reward
+    assert torch.allclose((buf.rewards.double() - ref)[buf.dones.logical_not()].abs().max(), torch.tensor(0.0, dtype=torch.float64, device="cuda"), atol=5.0)
+    assert bool(torch.isfinite(buf.rewards).all()) and buf.stats()["env_steps"] == 24 * 8192
+    env.close()
