@@ -55,9 +55,9 @@ struct qg_batch {
     int *d_perm, *d_bin_count;   // d_bin_count: [2][QG_NBINS] = counts, cursors
     unsigned char* d_bin_key;
     bool perm_valid, binning;
-    // pinned + device staging for the host-buffer path
-    float *h_act, *h_obs, *h_rew, *d_act, *d_obs, *d_rew;
-    unsigned char *h_term, *d_term;
+    // device staging for the host-buffer path (qg_step_host)
+    float *d_act, *d_obs, *d_rew;
+    unsigned char* d_term;
     // WalkingQuadrupedEnv reward stack (qg_walk_*)
     bool walk_on;
     QgWalkState walk;
@@ -474,8 +474,8 @@ extern "C" int qg_batch_create(const qg_model* m, int n_envs, int device, qg_bat
     memset(&b->po, 0, sizeof b->po);
     memset(&b->walk, 0, sizeof b->walk);
     memset(&b->wopts, 0, sizeof b->wopts);
-    b->h_act = b->h_obs = b->h_rew = b->d_act = b->d_obs = b->d_rew = nullptr;
-    b->h_term = b->d_term = nullptr;
+    b->d_act = b->d_obs = b->d_rew = nullptr;
+    b->d_term = nullptr;
     b->n = n_envs;
     b->device = device;
     default_opts(m, b->opts);
@@ -528,10 +528,6 @@ extern "C" void qg_batch_destroy(qg_batch* b) {
     cudaSetDevice(b->device);
     cudaFree(b->d_model); cudaFree(b->d_verts); cudaFree(b->d_vert_adj); cudaFree(b->d_adj4); cudaFree(b->d_vert_cadj); cudaFree(b->d_cadj4);
     cudaFree(b->d_state); cudaFree(b->d_ctr); cudaFree(b->d_perm); cudaFree(b->d_bin_count); cudaFree(b->d_bin_key);
-    if (b->h_act) cudaFreeHost(b->h_act);
-    if (b->h_obs) cudaFreeHost(b->h_obs);
-    if (b->h_rew) cudaFreeHost(b->h_rew);
-    if (b->h_term) cudaFreeHost(b->h_term);
     cudaFree(b->d_act); cudaFree(b->d_obs); cudaFree(b->d_rew); cudaFree(b->d_term);
     for (void* p : b->walk_allocs) cudaFree(p);
     delete b;

@@ -266,8 +266,6 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
         const bool do_reset = term && opts.auto_reset;
         if (valid) {
         if (do_reset) {
-            float z[3] = {0.f, 0.f, 0.f};
-            (void)z;
             float* o = obs + (size_t)env * 33;
             for (int k = leg; k < 33; k += 4) o[k] = 0.f;
         } else {

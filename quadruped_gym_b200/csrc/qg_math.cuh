@@ -46,12 +46,7 @@ DI s3 rot_sym(const m3& R, const s3& S) {
     return o;
 }
 
-DI float qsum(float v, unsigned qm) {
-    v += __shfl_xor_sync(qm, v, 1);
-    v += __shfl_xor_sync(qm, v, 2);
-    return v;
-}
-DI v3 qsum(v3 v, unsigned qm) { return V3(qsum(v.x, qm), qsum(v.y, qm), qsum(v.z, qm)); }
+// integer quad sum by xor-shuffles (used a handful of times per launch; the hot float reductions go through QuadRed)
 DI int qsumi(int v, unsigned qm) {
     v += __shfl_xor_sync(qm, v, 1);
     v += __shfl_xor_sync(qm, v, 2);

@@ -607,3 +607,52 @@ def test_full_size_properties_and_rollout_buffer(Vec):
     assert torch.allclose((buf.rewards.double() - ref)[buf.dones.logical_not()].abs().max(), torch.tensor(0.0, dtype=torch.float64, device="cuda"), atol=5.0)
     assert bool(torch.isfinite(buf.rewards).all()) and buf.stats()["env_steps"] == 24 * 8192
     env.close()
+
+
+@pytest.mark.parametrize("n", [1, 3, 63, 65, 1000])
+def test_ragged_batch_sizes_and_state_roundtrip(Vec, oracle_model, n):
+    """Batch sizes that do not fill a quad-of-quads / warp / block: tail quads must not disturb their neighbours,
+    get_state(set_state(x)) == x, masked reset touches only the masked environments."""
+    env = Vec(n, "cuda:0", auto_reset=False)
+    env.reset()
+    rng = np.random.default_rng(n)
+    qpos = env.data.qpos.cpu().numpy()
+    qpos[:, 7:] += rng.uniform(-0.2, 0.2, (n, 12)).astype(np.float32)
+    qvel = rng.normal(size=(n, 18)).astype(np.float32)
+    act = rng.uniform(-0.3, 0.3, (n, 12)).astype(np.float32)
+    tm = rng.uniform(0, 5, n)
+    env.set_state(qpos=qpos, qvel=qvel, act=act, time=tm)
+    assert np.array_equal(env.data.qpos.cpu().numpy(), qpos) and np.array_equal(env.data.qvel.cpu().numpy(), qvel)
+    assert np.array_equal(env.data.act.cpu().numpy(), act) and np.array_equal(env.data.time.cpu().numpy(), tm)
+    a = rng.uniform(-1, 1, (n, 12)).astype(np.float32)
+    obs, rew, term, trunc, _ = env.step(torch.from_numpy(a).cuda())
+    assert obs.shape == (n, 33) and bool(torch.isfinite(obs).all()) and not bool(trunc.any())
+    # last environment against the oracle (it sits next to the shadow quads of the tail)
+    d = OracleData(oracle_model)
+    d.set_state(qpos[-1].astype(np.float64), qvel[-1].astype(np.float64), act[-1].astype(np.float64), np.zeros(18), tm[-1], np.zeros(12))
+    d.env_step(a[-1].astype(np.float64), 4)
+    err = np.abs(obs[-1].cpu().numpy() - d.sensordata)
+    err[12:15] /= max(1.0, np.abs(d.qacc).max())
+    assert err.max() < 1e-4
+    mask = torch.zeros(n, dtype=torch.bool)
+    mask[::2] = True
+    before = env.data.qpos.clone()
+    env.reset(mask=mask.cuda())
+    after = env.data.qpos
+    assert torch.equal(after[~mask.cuda()], before[~mask.cuda()])
+    assert np.allclose(after[mask.cuda()].cpu().numpy()[:, :7], [0, 0, 0.13, 1, 0, 0, 0])
+    assert float(env.data.time[0]) == 0.0
+    env.close()
+
+
+def test_argument_errors(Vec):
+    env = Vec(4, "cuda:0")
+    env.frame_skip = 0
+    with pytest.raises(ValueError):
+        env.step(torch.zeros((4, 12), device="cuda"))          # QG_EINVAL: frame_skip must be >= 1
+    env.frame_skip = 4
+    with pytest.raises(RuntimeError):
+        env.step(torch.zeros((5, 12), device="cuda"))          # wrong batch size
+    with pytest.raises(NotImplementedError):
+        Vec(2, "cuda:0", render_mode="human")                  # rendering is out of scope
+    env.close()
