@@ -299,6 +299,8 @@ void qgo_reset(const qgo_model* m, qgo_data* d) {
 
 /* ------------------------------------------------------------------ position stage */
 
+/* mj_kinematics: body frames from qpos (stage of mj_step, reference call site /root/reference/src/envs/quadruped.py:165;
+   tree and joint conventions from /root/reference/src/models/quadruped/quadruped.xml:62-142) */
 static void kinematics(const qgo_model* m, qgo_data* d) {
     double* R0 = d->xmat;
     memset(d->xpos, 0, 3 * sizeof(double));
@@ -440,7 +442,8 @@ static void jac_point(const qgo_model* m, const qgo_data* d, double* jp, int bod
     }
 }
 
-/* plane (z = plane_z, normal +z) vs convex mesh: support vertex + up to 3 hull-graph neighbours */
+/* mjc_PlaneConvex restated: floor plane (/root/reference/src/models/quadruped/scene.xml:21) vs the convex hull of every
+   robot mesh geom (quadruped.xml:8,145-150): support vertex + up to 3 hull-graph neighbours */
 static void collision(const qgo_model* m, qgo_data* d) {
     double pz = m->opt_f[7];
     int rule_first_only = m->opt_i[4];
@@ -520,7 +523,7 @@ static void impedance(const double* solref, const double* solimp, double timeste
     *imp = v;
 }
 
-/* joint-limit rows then pyramidal contact rows (mj_makeConstraint) */
+/* mj_makeConstraint: joint-limit rows (ranges of quadruped.xml:25,30,35) then pyramidal or elliptic contact rows */
 static void make_constraint(const qgo_model* m, qgo_data* d) {
     int nv = m->nv, ne = 0;
     double h = m->opt_f[0];
@@ -637,6 +640,7 @@ static ellzone ell_eval(const qgo_model* m, const qgo_data* d, int i, double j0,
 
 /* ------------------------------------------------------------------ velocity stage */
 
+/* mj_comVel: spatial velocities and cdof_dot (stage of mj_step, quadruped.py:165) */
 static void com_vel(const qgo_model* m, qgo_data* d) {
     memset(d->cvel, 0, 6 * sizeof(double));
     for (int b = 1; b < m->nbody; b++) {
@@ -660,6 +664,8 @@ static void com_vel(const qgo_model* m, qgo_data* d) {
     }
 }
 
+/* mj_rne(flg_acc = 0): Coriolis, centrifugal and gravity forces (stage of mj_step, quadruped.py:165; gravity is the
+   MuJoCo default since quadruped.xml:4 sets only the integrator) */
 static void rne_bias(const qgo_model* m, qgo_data* d) {
     double cacc[QGO_MAXNBODY * 6], cfrc[QGO_MAXNBODY * 6];
     memset(cacc, 0, sizeof cacc);
@@ -689,7 +695,8 @@ static void rne_bias(const qgo_model* m, qgo_data* d) {
     }
 }
 
-/* position servo with first-order activation filter (mj_fwdActuation) */
+/* mj_fwdActuation for the 12 <position> servos (/root/reference/src/models/quadruped/quadruped.xml:10-17,26-36,156-172):
+   ctrl clamp, first-order activation filter, affine bias, force clamp, gear */
 static void actuation(const qgo_model* m, qgo_data* d) {
     memset(d->qfrc_actuator, 0, sizeof(double) * m->nv);
     for (int i = 0; i < m->nu; i++) {
@@ -796,6 +803,8 @@ static double linesearch(const qgo_model* m, qgo_data* d, const double* jar, con
     return a;
 }
 
+/* mj_solNewton restated: primal Newton with exact line search (solver = MuJoCo default; quadruped.xml:4 does not override
+   it; stage of mj_step, quadruped.py:165) */
 static void solve_newton(const qgo_model* m, qgo_data* d) {
     int nv = m->nv, ne = d->nefc;
     double Ma[QGO_MAXNV], grad[QGO_MAXNV], search[QGO_MAXNV], Mv[QGO_MAXNV];
@@ -900,6 +909,7 @@ static void solve_newton(const qgo_model* m, qgo_data* d) {
     }
 }
 
+/* mj_fwdConstraint: warm start selection, then the solver (stage of mj_step, quadruped.py:165) */
 static void fwd_constraint(const qgo_model* m, qgo_data* d) {
     int nv = m->nv, ne = d->nefc;
     g_model_for_cone = m;
@@ -937,6 +947,8 @@ static void fwd_constraint(const qgo_model* m, qgo_data* d) {
 
 /* ------------------------------------------------------------------ forward / step */
 
+/* mj_sensorPos/Vel/Acc for the sensor block of /root/reference/src/models/quadruped/quadruped.xml:174-217, read by
+   _get_obs at /root/reference/src/envs/quadruped.py:141-143 */
 static void sensors(const qgo_model* m, qgo_data* d) {
     /* site FRAME sits at the free body's origin with identity orientation (quadruped.xml:69) */
     const double* R = d->xmat + 9;
@@ -987,6 +999,7 @@ static int bad_state(const double* x, int n) {
     return 0;
 }
 
+/* mj_implicit (integrator="implicitfast", /root/reference/src/models/quadruped/quadruped.xml:4) followed by mj_advance */
 static void integrate(const qgo_model* m, qgo_data* d) {
     int nv = m->nv;
     double h = m->opt_f[0], qacc[QGO_MAXNV], H[QGO_MAXNV * QGO_MAXNV];

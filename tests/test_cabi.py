@@ -94,3 +94,13 @@ def test_product_does_not_import_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, re.M), f
                 assert "libqgoracle" not in txt and "qg_oracle.h" not in txt and "qgo_step" not in txt, f
+
+
+def test_missing_extension_fails_loudly(tmp_path):
+    """No silent fallback: with the .so absent, loading the library raises (checked in a fresh interpreter)."""
+    import subprocess, sys
+    code = ("import os, sys; sys.path.insert(0, %r); os.environ['QG_LIB'] = %r\n"
+            "from quadruped_gym_b200 import _lib\n"
+            "try:\n    _lib.lib()\nexcept _lib.QuadGymLibraryError as e:\n    print('RAISED', 'no CPU fallback' in str(e))\n") % (ROOT, str(tmp_path / "nope.so"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.stdout.strip() == "RAISED True", out.stdout + out.stderr
