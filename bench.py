@@ -158,8 +158,8 @@ def flops_per_physics_step(c):
     """SURVEY.md App. E work model evaluated with the kernel's own counters (per physics env-step)."""
     n = max(c["physics_steps"], 1)
     nc, nefc, nit, v = c["contacts"] / n, c["efc_rows"] / n, c["newton_iters"] / n, c["verts_tested"] / n
-    n_act = 0.5 * nefc
-    return 13000 + 5 * v + 470 * nc + nit * (68 * nefc + 342 * n_act + 2600), dict(contacts=nc, efc_rows=nefc, newton_iters=nit, verts_tested=v, ls_evals=c["ls_evals"] / n)
+    n_act = c.get("active_rows", 0.5 * c["efc_rows"]) / n
+    return 13000 + 5 * v + 470 * nc + nit * (68 * nefc + 342 * n_act + 2600), dict(contacts=nc, efc_rows=nefc, active_rows=n_act, newton_iters=nit, verts_tested=v, ls_evals=c["ls_evals"] / n)
 
 
 def run_ours(a):

@@ -81,6 +81,7 @@ typedef struct qg_counters {
     unsigned long long diverged;        /* envs reset by the non-finite / >1e10 guard */
     unsigned long long contact_overflow;/* contacts dropped because a lane's table was full */
     unsigned long long episodes;        /* terminations seen by qg_step */
+    unsigned long long active_rows;     /* rows with non-zero force at the solver's final point */
 } qg_counters;
 
 const char* qg_last_error(void);

@@ -42,7 +42,7 @@ class QuadGymLibraryError(RuntimeError):
 class Counters(C.Structure):
     _fields_ = [(n, C.c_ulonglong) for n in (
         "physics_steps", "contacts", "efc_rows", "newton_iters", "ls_evals", "verts_tested", "diverged",
-        "contact_overflow", "episodes")]
+        "contact_overflow", "episodes", "active_rows")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

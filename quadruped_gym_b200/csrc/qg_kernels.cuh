@@ -23,7 +23,7 @@
 
 struct QgCounters {
     unsigned long long physics_steps, contacts, efc_rows, newton_iters, ls_evals, verts_tested, diverged,
-        contact_overflow, episodes;
+        contact_overflow, episodes, active_rows;
 };
 
 DI float4 ldS(const float4* S, int plane, int N, int env) { return S[(size_t)plane * N + env]; }
@@ -161,7 +161,7 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
     const int env = perm ? perm[slot] : slot;
     if (!valid) { dbg.qacc = dbg.qacc_smooth = dbg.qfrc_bias = dbg.M = dbg.sensordata = nullptr; dbg.counts = nullptr; }
     const unsigned qm = 0xFu << (threadIdx.x & 28);
-    unsigned long long cv[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long cv[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     QuadRed qr;
     qr.s = sred;
     qr.lane = threadIdx.x & 31;
@@ -182,7 +182,7 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
         }
 
         StepStats st;
-        st.ncon = st.nefc = st.niter = st.nls = st.nvert = st.overflow = 0;
+        st.ncon = st.nefc = st.niter = st.nls = st.nvert = st.overflow = st.nact = 0;
         st.last_nefc = st.last_iter = 0;
         int diverged = 0;
         SensorOut so;
@@ -297,6 +297,7 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
         cv[0] = leg == 0 ? frame_skip : 0; cv[1] = st.ncon; cv[2] = st.nefc; cv[3] = st.niter;
         cv[4] = leg == 0 ? st.nls : 0; cv[5] = st.nvert; cv[6] = diverged; cv[7] = st.overflow;
         cv[8] = (leg == 0 && term) ? 1 : 0;
+        cv[9] = st.nact;
         }
         if (bin_key) {   // key of the next launch's binning: which legs were in contact, and the Newton iterations needed
             int pattern = qsumi((C.n > 0 ? 1 : 0) << leg, qm);
@@ -308,7 +309,7 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
     {
         unsigned long long* out = reinterpret_cast<unsigned long long*>(ctr);
 #pragma unroll
-        for (int i = 0; i < 9; ++i) {
+        for (int i = 0; i < 10; ++i) {
             unsigned long long x = cv[i];
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);

@@ -40,7 +40,7 @@ struct SensorOut {
 };
 
 struct StepStats {
-    int ncon, nefc, niter, nls, nvert, overflow;
+    int ncon, nefc, niter, nls, nvert, overflow, nact;   // nact: active rows at the solver's final point
     int last_nefc, last_iter;   // of the most recent physics step (env totals): the binning key of the next launch
 };
 
@@ -636,7 +636,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
     for (int i = 0; i < 21; ++i) Hc[i] = 0.f;
 #pragma unroll
     for (int i = 0; i < 3; ++i) { rl[i] = fsl[i]; fcl[i] = 0.f; }
-    int phase = 0, iter = 0;
+    int phase = 0, iter = 0, nact_last = 0;
     float cost_old = 0.f, impr_est = 0.f;
     bool done = false;
 #pragma unroll 1
@@ -852,6 +852,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
             float cost = 0.f;
             v3 Fb = V3(0, 0, 0), Nb = V3(0, 0, 0);
             float tau[3] = {0.f, 0.f, 0.f};
+            nact_last = 0;
 #pragma unroll 1
             for (int c = 0; c < nc; ++c) {
                 float D = C.D[c], mu = C.mu[c];
@@ -861,12 +862,14 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                 if (CONE) {
                     EllZ z = ell_eval(C.jar[0][c], C.jar[1][c], C.jar[2][c], mu, mus, D, D * impr);
                     cost += z.cost;
+                    nact_last += z.zone ? 3 : 0;
                     fc = fma3(z.f0, up, fma3(z.f1, ty, (-z.f2) * tx));   // rows: n = up, t1 = ty, t2 = -tx
                 } else {
                     float j0 = C.jar[0][c], j1 = C.jar[1][c], j2 = C.jar[2][c], j3 = C.jar[3][c];
                     float f0 = j0 < 0.f ? -D * j0 : 0.f, f1 = j1 < 0.f ? -D * j1 : 0.f;
                     float f2 = j2 < 0.f ? -D * j2 : 0.f, f3 = j3 < 0.f ? -D * j3 : 0.f;
                     cost -= 0.5f * (f0 * j0 + f1 * j1 + f2 * j2 + f3 * j3);
+                    nact_last += (j0 < 0.f) + (j1 < 0.f) + (j2 < 0.f) + (j3 < 0.f);
                     // force vector in B: sum f_k w_k,  w = up +- mu*ty, up -+ mu*tx
                     fc = fma3(f0 + f1 + f2 + f3, up, fma3(mu * (f0 - f1), ty, (-mu * (f2 - f3)) * tx));
                 }
@@ -881,6 +884,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
             for (int k = 0; k < 3; ++k) {
                 if (lsgn[k] != 0.f && ljar[k] < 0.f) {
                     float f = -lD[k] * ljar[k];
+                    nact_last++;
                     cost -= 0.5f * f * ljar[k];
                     tau[k] += lsgn[k] * f;
                 }
@@ -1020,6 +1024,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
     st.niter += (leg == 0) ? iter : 0;
     st.last_nefc = nefc;
     st.last_iter = iter;
+    st.nact += nact_last;
 
     // ---- sensors of this forward pass (pre-integration state, solver qacc)
     if (want_sensors) {
