@@ -6,7 +6,8 @@ Mirrors the interface of the reference's base environment
 surface that reward callables touch (walking_quad.py:19-20,56,93,142,253,393).  All N environments
 live in device memory owned by libquadgym; one ``step`` is ONE kernel launch.
 
-Rendering (quadruped.py:184-316) is out of scope: ``render_mode`` other than ``None`` raises.
+Rendering (quadruped.py:184-316) is out of scope except for a thin bridge: ``render_mode="rgb_array"`` copies one
+environment's qpos to a CPU ``mujoco.MjData`` and uses MuJoCo's renderer (only where the ``mujoco`` wheel is installed).
 """
 from __future__ import annotations
 
@@ -128,8 +129,10 @@ class VecQuadrupedEnv:
                  termination_fns: Optional[dict] = None, use_default_termination: bool = True,
                  auto_reset: bool = True, seed: int = 0, env_offset: int = 0, random_init: bool = False,
                  mesh_inertia: str = "legacy", model_blob: Optional[bytes] = None, **unused_render_kwargs):
-        if render_mode is not None:
-            raise NotImplementedError("rendering is out of scope for the B200 batched path (render_mode must be None)")
+        if render_mode not in (None, "rgb_array"):
+            raise NotImplementedError("only render_mode=None or 'rgb_array' (MuJoCo bridge, needs the mujoco wheel) is supported")
+        self.render_mode = render_mode
+        self._renderer = None
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.QuadGymLibraryError("VecQuadrupedEnv needs a CUDA device; there is no CPU fallback")
@@ -268,6 +271,30 @@ class VecQuadrupedEnv:
                                            self._h_term.ctypes.data_as(C.c_void_p), self._stream()), "qg_step_host")
         return self._h_obs, self._h_rew, self._h_term.astype(bool), np.zeros(self.num_envs, dtype=bool), {}
 
+    def render(self, index: int = 0, width: int = 720, height: int = 480):
+        """Rendering bridge: copy ONE environment's qpos to a CPU ``mujoco.MjData`` and render it with
+        MuJoCo's own renderer, camera as in the reference (quadruped.py:77-86,250-306).  Needs the ``mujoco`` wheel and
+        an MJCF ``model_path``; the batched physics never depends on it."""
+        if self.render_mode != "rgb_array":
+            return None
+        try:
+            import mujoco
+        except ImportError as e:  # pragma: no cover - mujoco is not installable in the build container
+            raise NotImplementedError("render() needs the `mujoco` wheel (CPU renderer bridge)") from e
+        if self._renderer is None:  # pragma: no cover
+            if not (self.model_path and str(self.model_path).endswith(".xml")):
+                raise ValueError("render() needs the env to be built from an MJCF model_path")
+            m = mujoco.MjModel.from_xml_path(self.model_path)
+            cam = mujoco.MjvCamera()
+            cam.distance, cam.elevation, cam.azimuth = 1.0, -30, 120
+            self._renderer = (m, mujoco.MjData(m), mujoco.Renderer(m, width=width, height=height), cam)
+        m, d, r, cam = self._renderer  # pragma: no cover
+        d.qpos[:] = self.data.qpos[index].double().cpu().numpy()
+        mujoco.mj_forward(m, d)
+        cam.lookat[:] = d.qpos[:3]
+        r.update_scene(d, camera=cam)
+        return r.render()
+
     # -- state access for parity tests -----------------------------------------------------------
     def set_state(self, qpos=None, qvel=None, act=None, qacc_warmstart=None, time=None, ctrl=None):
         def prep(x, k, dt=torch.float32):
@@ -319,7 +346,7 @@ class QuadrupedEnv(_EnvBase):
     Reward / termination callables are zero-argument Python functions over ``env.data`` / ``env.model``
     as in the reference; fused specs from ``rewards`` are accepted too."""
 
-    metadata = {"render_modes": [], "render_fps": 30}
+    metadata = {"render_modes": ["rgb_array"], "render_fps": 30}
 
     def __init__(self, model_path: Optional[str] = None, max_time: float = 10.0, frame_skip: int = 4,
                  render_mode: str = None, width: int = 720, height: int = 480, render_fps: int = 30,
@@ -368,7 +395,7 @@ class QuadrupedEnv(_EnvBase):
         return obs[0].double().cpu().numpy(), float(rew[0]), bool(term[0]), False, {"time": t, "reward_components": comps}
 
     def render(self):
-        return None
+        return self.vec.render(0)
 
     def close(self):
         self.vec.close()

@@ -654,5 +654,12 @@ def test_argument_errors(Vec):
     with pytest.raises(RuntimeError):
         env.step(torch.zeros((5, 12), device="cuda"))          # wrong batch size
     with pytest.raises(NotImplementedError):
-        Vec(2, "cuda:0", render_mode="human")                  # rendering is out of scope
+        Vec(2, "cuda:0", render_mode="human")                  # only the rgb_array MuJoCo bridge exists
+    e2 = Vec(2, "cuda:0", render_mode="rgb_array")
+    try:
+        import mujoco  # noqa: F401
+    except ImportError:
+        with pytest.raises(NotImplementedError):
+            e2.render()                                        # bridge needs the mujoco wheel: fails loudly without it
+    e2.close()
     env.close()
