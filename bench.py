@@ -175,7 +175,11 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("QG_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION and above
+        if "QG_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["QG_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=dev)
     envs, fs, max_time, desc = WORKLOADS[a.workload]
     if a.envs:
