@@ -349,6 +349,13 @@ extern "C" int qg_model_load(const void* blob, size_t nbytes, qg_model** out) {
         m->cadj = m->adj;
         mesh_cadj0 = mesh_adj0;
     }
+    // the two list offsets of a vertex ride in the .w of its float4 (climb list in the low, hull list in the high half):
+    // the support search reads them with the vertex instead of through one more dependent load per hop
+    for (int i = 0; i < nvert; ++i) {
+        if (m->vert_cadj[i] > 0xffff || m->vert_adj[i] > 0xffff) BADMODEL("hull graph too large for 16-bit list offsets");
+        unsigned w = (unsigned)m->vert_cadj[i] | ((unsigned)m->vert_adj[i] << 16);
+        memcpy(&m->verts[4 * (size_t)i + 3], &w, 4);
+    }
     c.nvert = nvert;
     if (nmesh > QG_MAXMESH) BADMODEL("too many meshes (%d > %d)", nmesh, QG_MAXMESH);
     // support-search start table: exhaustive argmin at the centre direction of every cube-map cell
@@ -510,7 +517,7 @@ extern "C" int qg_batch_create(const qg_model* m, int n_envs, int device, qg_bat
     // weak predictor there), for 2 extra launches per step -- off by default
     b->binning = false;
     if (const char* ev = getenv("QG_BINNING")) b->binning = atoi(ev) != 0;   // tests / experiments
-    b->smem = ((sizeof(QgModelC) + 15) & ~size_t(15)) + sizeof(float4) * nv + sizeof(float) * QG_QR_SLOTS * 32 * (QG_BLOCK / 32);
+    b->smem = ((sizeof(QgModelC) + 15) & ~size_t(15)) + sizeof(float4) * nv + sizeof(float) * (QG_QR_SLOTS * 32 + QG_CQ_FLOATS) * (QG_BLOCK / 32);
     CUDA_OK(cudaFuncSetAttribute(qg_step_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
     CUDA_OK(cudaFuncSetAttribute(qg_step_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
     CUDA_OK(cudaFuncSetAttribute(qg_step_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));

@@ -141,7 +141,8 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
     QgModelC& P = *reinterpret_cast<QgModelC*>(smem);
     float4* sverts = reinterpret_cast<float4*>(smem + ((sizeof(QgModelC) + 15) & ~size_t(15)));
     // per-warp scratch of the quad all-reduce, behind the vertex table
-    float* sred = reinterpret_cast<float*>(sverts + gm->nvert) + (threadIdx.x >> 5) * (QG_QR_SLOTS * 32);
+    float* sred = reinterpret_cast<float*>(sverts + gm->nvert) + (threadIdx.x >> 5) * (QG_QR_SLOTS * 32 + QG_CQ_FLOATS);
+    const WarpQueue wq = warp_queue(sred + QG_QR_SLOTS * 32);   // collision queue of this warp, behind its reduction rows
     {
         const int4* src = reinterpret_cast<const int4*>(gm);
         int4* dst = reinterpret_cast<int4*>(smem);
@@ -199,7 +200,7 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
                 L.ctrl[0] = c0; L.ctrl[1] = c1; L.ctrl[2] = c2;
                 diverged += (leg == 0);
             }
-            physics_step<DEBUG, CONE>(P, sverts, vert_adj, adj4, vert_cadj, cadj4, L, leg, qr, max_iter, ls_iter, s == frame_skip - 1, so,
+            physics_step<DEBUG, CONE>(P, sverts, vert_adj, adj4, vert_cadj, cadj4, L, leg, qr, wq, max_iter, ls_iter, s == frame_skip - 1, so,
                                 st, C, dbg, env);
         }
 

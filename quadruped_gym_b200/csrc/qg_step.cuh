@@ -14,13 +14,13 @@
 //     of the owning leg.  M and the Newton Hessian H = M + J^T D J therefore share one "arrow"
 //     sparsity pattern: a 6x6 base block, four 6x3 couplings and four 3x3 leg blocks.  Each lane
 //     eliminates its own 3x3 block in registers; the 6x6 Schur complement is summed across the
-//     quad with two xor-shuffles per value and factorised redundantly by all four lanes.
-// No shared-memory scratch, no __syncthreads and no cross-quad communication on the step path.
-//
-// Code-size discipline (the first version was 270 KB of SASS and stalled on instruction fetch): the
-// collision code exists once (rolled loop over the lane's geoms), and the three SPD solves of a step
-// (unconstrained acceleration, Newton direction, implicit integration) share ONE inlined arrow_solve
-// inside a small phase machine.
+//     quad through a shared-memory all-reduce (QuadRed) and factorised redundantly by all four lanes.
+// The kernel is latency bound (255 registers -> 8 warps per SM), so the code is shaped by
+// three rules: keep the SASS small and shared between warps (ONE inlined arrow_solve inside a phase machine serves
+// the three SPD solves of a step; rolled loops; the warps of a block walk the solver loop together through
+// __syncthreads_or so that one instruction-cache fill serves all of them), keep serial dependency chains short
+// (MUFU reciprocals / square roots, list offsets fetched with the vertex, 4 neighbours per trip), and keep lanes
+// busy (the collision narrow phase is balanced over the warp through a shared-memory queue).
 #pragma once
 #include "qg_math.cuh"
 #include "qg_model.h"
@@ -113,8 +113,7 @@ DI void arrow_solve(const float* All, const float* Abl, const float* Alocal, con
         float s = A[IX6(j, j)];
 #pragma unroll
         for (int k = 0; k < j; ++k) s -= A[IX6(j, k)] * A[IX6(j, k)];
-        s = sqrtf(fmaxf(s, 1e-12f));
-        inv[j] = 1.f / s;
+        inv[j] = rsqrtf(fmaxf(s, 1e-12f));   // only 1/L_jj is ever used
 #pragma unroll
         for (int i = j + 1; i < 6; ++i) {
             float t = A[IX6(i, j)];
@@ -249,19 +248,136 @@ __device__ __noinline__ float2 sincos_ni(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// plane-vs-hull collision of all geoms this lane owns (mjc_PlaneConvex restated).
-//   pass 1: oriented-box cull of every geom (20 flops each) -> bit mask of candidates;
-//   pass 2: per candidate, hill-climbing support search on the hull graph (exact for a convex hull; start
-//           vertex from a cube-map table of the search direction; neighbour lists are padded to int4
-//           groups so that four neighbours are fetched and evaluated per step), then up to 3 hull-graph
-//           neighbours of the support vertex become extra contacts.
-// Lanes walk their own candidate lists in lockstep, so the j-th candidates of all lanes overlap.
+// plane-vs-hull collision (mjc_PlaneConvex restated), balanced over the WARP.
+//   pass 1 (every lane, its own geoms): oriented-box cull (20 flops each).  Survivors are pushed onto a per-warp
+//           queue in shared memory as (search direction and centre height in the MESH frame, leg, geom).
+//   pass 2 (any lane, any queue entry): hill-climbing support search on the polytope-edge graph (exact for a convex
+//           hull; start vertex from a cube-map table of the direction; neighbour lists padded to int4 groups), then
+//           up to 3 hull-graph neighbours of the support vertex become extra contacts.  Works in the mesh frame only
+//           (heights and mutual distances are rigid-motion invariant), so it needs nothing of the owner's kinematics.
+//   pass 3 (owner): transforms the reported vertices to the base frame and appends the contact records.
+// Only 1 lane in 4 has a candidate at any time (legs in the air, culled geoms); with lane-local narrow phases the
+// warp ran pass 2 at 7 of 32 lanes.  Contacts reach the owner in (geom, candidate) order whatever lane produced them,
+// so results do not depend on the balancing.
 // `fr` holds the lane's 4 link frames (level 0 = base): rotation (row major, link -> B) and position.
+#define QG_CQ_CAP 64                                   // queue entries per warp (32 carried over + 32 pushed)
+#define QG_CQ_FLOATS (QG_CQ_CAP * 5 + 32 * 17)         // queue: float4 + meta; results: 4 float4 + count per slot
+struct WarpQueue {
+    float4* qd;    // [QG_CQ_CAP] (dl.x, dl.y, dl.z, zc)
+    int* qmeta;    // [QG_CQ_CAP] leg | geom << 2
+    float4* res;   // [32][4]     (vertex in the mesh frame, distance to the plane)
+    int* rcnt;     // [32]
+};
+DI WarpQueue warp_queue(float* w) {
+    WarpQueue q;
+    q.qd = reinterpret_cast<float4*>(w);
+    q.qmeta = reinterpret_cast<int*>(w + 4 * QG_CQ_CAP);
+    q.res = reinterpret_cast<float4*>(w + 5 * QG_CQ_CAP);
+    q.rcnt = reinterpret_cast<int*>(w + 5 * QG_CQ_CAP + 32 * 16);
+    return q;
+}
+
+// pass 2 for one queue entry; returns the number of contacts written to out[0..3]
+DI int narrow_phase(const QgModelC& P, const float4* __restrict__ verts, const int* __restrict__ vert_adj,
+                    const int4* __restrict__ adj4, const int* __restrict__ vert_cadj, const int4* __restrict__ cadj4,
+                    float4 e4, int meta, float4* out, int& nvert) {
+    const QgGeomC& G = P.geom[meta & 3][meta >> 2];
+    const v3 dl = V3(e4.x, e4.y, e4.z);
+    const float zc = e4.w, margin = G.margin;
+    const float4* __restrict__ vt = verts + G.vert0;
+    const int4* __restrict__ el = adj4 + G.edge0;
+    const int4* __restrict__ cl = cadj4 + G.cedge0;
+    int best;
+    {
+        float ax = fabsf(dl.x), ay = fabsf(dl.y), az = fabsf(dl.z);
+        int a = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
+        float dm = a == 0 ? dl.x : (a == 1 ? dl.y : dl.z);
+        float du = a == 0 ? dl.y : (a == 1 ? dl.z : dl.x);
+        float dw = a == 0 ? dl.z : (a == 1 ? dl.x : dl.y);
+        float inv = 1.f / fmaxf(fabsf(dm), 1e-20f);
+        int iu = min(QG_DIRRES - 1, max(0, (int)((du * inv + 1.f) * (0.5f * QG_DIRRES))));
+        int iv = min(QG_DIRRES - 1, max(0, (int)((dw * inv + 1.f) * (0.5f * QG_DIRRES))));
+        best = P.dir_start[G.mesh][((2 * a + (dm > 0.f ? 1 : 0)) * QG_DIRRES + iu) * QG_DIRRES + iv];
+    }
+    float4 vbest = vt[best];   // .w carries the vertex' list offsets: climb graph | hull graph << 16 (int4 units)
+    float hbest = fmaf(dl.x, vbest.x, fmaf(dl.y, vbest.y, dl.z * vbest.z));
+    int nev = 1;
+#pragma unroll 1
+    for (;;) {
+        const int4* __restrict__ e = cl + (__float_as_int(vbest.w) & 0xffff);
+        bool moved = false;
+#pragma unroll 1
+        for (;;) {
+            int4 nb = __ldg(e++);
+            float4 v0 = vt[max(nb.x, 0)], v1 = vt[max(nb.y, 0)], v2 = vt[max(nb.z, 0)], v3_ = vt[max(nb.w, 0)];
+            float h0 = fmaf(dl.x, v0.x, fmaf(dl.y, v0.y, dl.z * v0.z));
+            float h1 = fmaf(dl.x, v1.x, fmaf(dl.y, v1.y, dl.z * v1.z));
+            float h2 = fmaf(dl.x, v2.x, fmaf(dl.y, v2.y, dl.z * v2.z));
+            float h3 = fmaf(dl.x, v3_.x, fmaf(dl.y, v3_.y, dl.z * v3_.z));
+            if (nb.x >= 0 && h0 < hbest) { hbest = h0; vbest = v0; best = nb.x; moved = true; }
+            if (nb.y >= 0 && h1 < hbest) { hbest = h1; vbest = v1; best = nb.y; moved = true; }
+            if (nb.z >= 0 && h2 < hbest) { hbest = h2; vbest = v2; best = nb.z; moved = true; }
+            if (nb.w >= 0 && h3 < hbest) { hbest = h3; vbest = v3_; best = nb.w; moved = true; }
+            nev += (nb.x >= 0) + (nb.y >= 0) + (nb.z >= 0) + (nb.w >= 0);
+            if (nb.w < 0) break;
+        }
+        if (!moved) break;
+    }
+    nvert += nev;
+    if (zc + hbest > margin) return 0;
+    // support vertex first, then its hull-graph neighbours in list order (up to 4 candidates per geom).  A neighbour
+    // qualifies if it is within the margin and not closer than the tolerance to the candidates already taken.  Lists
+    // can be long (fan centres of flat faces: up to 104 neighbours) and nearly all entries fail the margin test, so
+    // four neighbours are fetched and tested per trip and the in-order bookkeeping runs only for the rare hits.
+    int cnt = 1, nout = 0;
+    float4 prev0 = vbest, prev1 = make_float4(0.f, 0.f, 0.f, 0.f), prev2 = prev1;
+    if (zc + hbest < margin) out[nout++] = make_float4(prev0.x, prev0.y, prev0.z, zc + hbest);  // rows only for dist < margin
+    const int4* __restrict__ e = el + ((unsigned)__float_as_int(vbest.w) >> 16);
+    const float tol2 = G.tol2;
+    const bool rule_first = P.rule_first != 0;
+    auto take = [&](float4 v, float dv) {
+        if (cnt >= 4) return;
+        float ax = v.x - prev0.x, ay = v.y - prev0.y, az = v.z - prev0.z;
+        bool ok = !(ax * ax + ay * ay + az * az < tol2);
+        if (!rule_first) {
+            float bx = v.x - prev1.x, by = v.y - prev1.y, bz = v.z - prev1.z;
+            float cx = v.x - prev2.x, cy = v.y - prev2.y, cz = v.z - prev2.z;
+            if (cnt > 1 && bx * bx + by * by + bz * bz < tol2) ok = false;
+            if (cnt > 2 && cx * cx + cy * cy + cz * cz < tol2) ok = false;
+        }
+        if (!ok) return;
+        if (cnt == 1) prev1 = v; else if (cnt == 2) prev2 = v;
+        cnt++;
+        if (dv < margin) out[nout++] = make_float4(v.x, v.y, v.z, dv);
+    };
+#pragma unroll 1
+    for (;;) {
+        int4 nb = __ldg(e++);
+        float4 v0 = vt[max(nb.x, 0)], v1 = vt[max(nb.y, 0)], v2 = vt[max(nb.z, 0)], v3_ = vt[max(nb.w, 0)];
+        float d0 = zc + fmaf(dl.x, v0.x, fmaf(dl.y, v0.y, dl.z * v0.z));
+        float d1 = zc + fmaf(dl.x, v1.x, fmaf(dl.y, v1.y, dl.z * v1.z));
+        float d2 = zc + fmaf(dl.x, v2.x, fmaf(dl.y, v2.y, dl.z * v2.z));
+        float d3 = zc + fmaf(dl.x, v3_.x, fmaf(dl.y, v3_.y, dl.z * v3_.z));
+        bool c0 = nb.x >= 0 && d0 <= margin, c1 = nb.y >= 0 && d1 <= margin;
+        bool c2 = nb.z >= 0 && d2 <= margin, c3 = nb.w >= 0 && d3 <= margin;
+        if (c0 || c1 || c2 || c3) {
+            if (c0) take(v0, d0);
+            if (c1) take(v1, d1);
+            if (c2) take(v2, d2);
+            if (c3) take(v3_, d3);
+        }
+        if (cnt >= 4 || nb.w < 0) break;
+    }
+    return nout;
+}
+
 DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const int* __restrict__ vert_adj,
                      const int4* __restrict__ adj4, const int* __restrict__ vert_cadj,
                      const int4* __restrict__ cadj4, int leg, const float* fr, v3 up, float zb, Contacts& C,
-                     StepStats& st) {
+                     StepStats& st, const WarpQueue& wq, int lane) {
     const int ng = P.ngeom[leg];
+    const int ngmax = max(max(P.ngeom[0], P.ngeom[1]), max(P.ngeom[2], P.ngeom[3]));
+    const unsigned lt = (1u << lane) - 1u;
     v3 dB[4];      // "up" in each link frame
     float hk[4];   // height of each link origin above the plane
 #pragma unroll
@@ -270,132 +386,102 @@ DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const 
         dB[k] = tmul(Rk, up);
         hk[k] = zb + dot(up, ld3(fr + 12 * k + 9));
     }
-    unsigned cand = 0;
+    // pass 3: contacts of the result slots in `mine` (ascending = geom order)
+    auto collect = [&](unsigned mine, unsigned gs) {
 #pragma unroll 1
-    for (int g = 0; g < ng; ++g) {
-        const QgGeomC& G = P.geom[leg][g];
-        const int lev = G.level;
-        v3 d = sel4(dB, lev);
-        float zc = (lev == 0 ? hk[0] : (lev == 1 ? hk[1] : (lev == 2 ? hk[2] : hk[3]))) + dot(d, ld3(G.pos));
-        v3 dl = tmul(ldm3(G.R), d);  // "up" in the mesh frame
-        float ext = fmaf(fabsf(dl.x), G.half[0], fmaf(fabsf(dl.y), G.half[1], fabsf(dl.z) * G.half[2]));
-        if (zc - ext <= G.margin) cand |= 1u << g;  // oriented-box cull (conservative; same contacts as any cull)
-    }
+        while (mine) {
+            const int slot = __ffs(mine) - 1;
+            mine &= mine - 1;
+            const int g = gs & 7;
+            gs >>= 3;
+            const int n = wq.rcnt[slot];
+            if (n == 0) continue;
+            const QgGeomC& G = P.geom[leg][g];
+            const int lev = G.level;
+            m3 Rk = ldm3(fr + 12 * lev);
+            v3 ctr = ld3(fr + 12 * lev + 9) + mul(Rk, ld3(G.pos));
+            m3 RB = matmul(Rk, ldm3(G.R));  // mesh frame -> B
 #pragma unroll 1
-    while (cand) {
-        const int g = __ffs(cand) - 1;
-        cand &= cand - 1;
-        const QgGeomC& G = P.geom[leg][g];
-        const int lev = G.level;
-        const float margin = G.margin;
-        v3 d = sel4(dB, lev);
-        float zc = (lev == 0 ? hk[0] : (lev == 1 ? hk[1] : (lev == 2 ? hk[2] : hk[3]))) + dot(d, ld3(G.pos));
-        v3 dl = tmul(ldm3(G.R), d);
-        const float4* __restrict__ vt = verts + G.vert0;
-        const int* __restrict__ va = vert_adj + G.vert0;
-        const int4* __restrict__ el = adj4 + G.edge0;
-        const int* __restrict__ vc = vert_cadj + G.vert0;
-        const int4* __restrict__ cl = cadj4 + G.cedge0;
-        int best;
-        {
-            float ax = fabsf(dl.x), ay = fabsf(dl.y), az = fabsf(dl.z);
-            int a = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
-            float dm = a == 0 ? dl.x : (a == 1 ? dl.y : dl.z);
-            float du = a == 0 ? dl.y : (a == 1 ? dl.z : dl.x);
-            float dw = a == 0 ? dl.z : (a == 1 ? dl.x : dl.y);
-            float inv = 1.f / fmaxf(fabsf(dm), 1e-20f);
-            int iu = min(QG_DIRRES - 1, max(0, (int)((du * inv + 1.f) * (0.5f * QG_DIRRES))));
-            int iv = min(QG_DIRRES - 1, max(0, (int)((dw * inv + 1.f) * (0.5f * QG_DIRRES))));
-            best = P.dir_start[G.mesh][((2 * a + (dm > 0.f ? 1 : 0)) * QG_DIRRES + iu) * QG_DIRRES + iv];
-        }
-        float hbest;
-        {
-            float4 v = vt[best];
-            hbest = fmaf(dl.x, v.x, fmaf(dl.y, v.y, dl.z * v.z));
-        }
-        int nev = 1;
-#pragma unroll 1
-        for (;;) {
-            const int4* __restrict__ e = cl + __ldg(vc + best);
-            int nxt = -1;
-            float hn = hbest;
-#pragma unroll 1
-            for (;;) {
-                int4 nb = __ldg(e++);
-                float4 v0 = vt[max(nb.x, 0)], v1 = vt[max(nb.y, 0)], v2 = vt[max(nb.z, 0)], v3_ = vt[max(nb.w, 0)];
-                float h0 = fmaf(dl.x, v0.x, fmaf(dl.y, v0.y, dl.z * v0.z));
-                float h1 = fmaf(dl.x, v1.x, fmaf(dl.y, v1.y, dl.z * v1.z));
-                float h2 = fmaf(dl.x, v2.x, fmaf(dl.y, v2.y, dl.z * v2.z));
-                float h3 = fmaf(dl.x, v3_.x, fmaf(dl.y, v3_.y, dl.z * v3_.z));
-                if (nb.x >= 0 && h0 < hn) { hn = h0; nxt = nb.x; }
-                if (nb.y >= 0 && h1 < hn) { hn = h1; nxt = nb.y; }
-                if (nb.z >= 0 && h2 < hn) { hn = h2; nxt = nb.z; }
-                if (nb.w >= 0 && h3 < hn) { hn = h3; nxt = nb.w; }
-                nev += (nb.x >= 0) + (nb.y >= 0) + (nb.z >= 0) + (nb.w >= 0);
-                if (nb.w < 0) break;
+            for (int k = 0; k < n; ++k) {
+                float4 v = wq.res[slot * 4 + k];
+                if (C.n < QG_MAXCON_LANE) {
+                    int c = C.n++;
+                    float dv = v.w;
+                    v3 xv = ctr + mul(RB, V3(v.x, v.y, v.z));
+                    v3 xc = fma3(-0.5f * dv, up, xv);
+                    float r = dv - G.margin;
+                    float imp = impedance(r, G.d0, G.dmax, G.width, G.mid, G.power);
+                    C.x[c] = xc.x; C.y[c] = xc.y; C.z[c] = xc.z;
+                    C.D[c] = 1.f / fmaxf(1e-15f, (1.f - imp) / imp * G.Rfac);
+                    C.mu[c] = G.mu;
+                    C.Bd[c] = G.B;
+                    C.Kr[c] = G.K * imp * r;
+                    C.lev[c] = lev;
+                } else st.overflow++;
             }
-            if (nxt < 0) break;
-            best = nxt;
-            hbest = hn;
         }
-        st.nvert += nev;
-        if (zc + hbest > margin) continue;
-        // support vertex first, then its hull-graph neighbours in list order (up to 4 contacts per geom)
-        m3 Rk = ldm3(fr + 12 * lev);
-        v3 ctr = ld3(fr + 12 * lev + 9) + mul(Rk, ld3(G.pos));
-        m3 RB = matmul(Rk, ldm3(G.R));  // mesh frame -> B
-        const int* __restrict__ e = reinterpret_cast<const int*>(el + __ldg(va + best));
-        int cnt = 0, cand_v = best;
-        // heights and mutual distances of the candidates are evaluated in the mesh frame (rigid-motion invariant);
-        // only vertices that become contacts are transformed to the base frame
-        float4 prev0 = make_float4(0.f, 0.f, 0.f, 0.f), prev1 = prev0, prev2 = prev0;
+    };
+    auto run_batch = [&](int n) {
+        __syncwarp();
+        if (lane < n) {
+            wq.rcnt[lane] = narrow_phase(P, verts, vert_adj, adj4, vert_cadj, cadj4, wq.qd[lane], wq.qmeta[lane],
+                                         wq.res + lane * 4, st.nvert);
+        }
+        __syncwarp();
+    };
+    int qn = 0;                          // warp-uniform queue length
+    unsigned mine = 0, mine_next = 0;    // this lane's entries: slots of the batch in flight / of the carry-over
+    unsigned gs = 0, gs_next = 0;        // their geom ids, 3 bits each, in slot order
+    int nm = 0, nm_next = 0;
 #pragma unroll 1
-        for (;;) {
-            float4 v = vt[cand_v];
-            float dv = zc + fmaf(dl.x, v.x, fmaf(dl.y, v.y, dl.z * v.z));
-            bool ok = (cnt == 0) || (dv <= margin);
-            if (ok && cnt > 0) {
-                float ax = v.x - prev0.x, ay = v.y - prev0.y, az = v.z - prev0.z;
-                if (ax * ax + ay * ay + az * az < G.tol2) ok = false;
-                if (!P.rule_first) {
-                    float bx = v.x - prev1.x, by = v.y - prev1.y, bz = v.z - prev1.z;
-                    float cx = v.x - prev2.x, cy = v.y - prev2.y, cz = v.z - prev2.z;
-                    if (cnt > 1 && bx * bx + by * by + bz * bz < G.tol2) ok = false;
-                    if (cnt > 2 && cx * cx + cy * cy + cz * cz < G.tol2) ok = false;
-                }
-            }
-            if (ok) {
-                if (cnt == 0) prev0 = v; else if (cnt == 1) prev1 = v; else if (cnt == 2) prev2 = v;
-                cnt++;
-                if (dv < margin) {  // includemargin: rows are instantiated only for dist < margin
-                    if (C.n < QG_MAXCON_LANE) {
-                        int c = C.n++;
-                        v3 xv = ctr + mul(RB, V3(v.x, v.y, v.z));
-                        v3 xc = fma3(-0.5f * dv, up, xv);
-                        float r = dv - margin;
-                        float imp = impedance(r, G.d0, G.dmax, G.width, G.mid, G.power);
-                        C.x[c] = xc.x; C.y[c] = xc.y; C.z[c] = xc.z;
-                        C.D[c] = 1.f / fmaxf(1e-15f, (1.f - imp) / imp * G.Rfac);
-                        C.mu[c] = G.mu;
-                        C.Bd[c] = G.B;
-                        C.Kr[c] = G.K * imp * r;
-                        C.lev[c] = lev;
-                    } else st.overflow++;
-                }
-            }
-            if (cnt >= 4) break;
-            int nb = __ldg(e++);
-            if (nb < 0) break;
-            cand_v = nb;
+    for (int g = 0; g < ngmax; ++g) {
+        bool pass = false;
+        float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g < ng) {
+            const QgGeomC& G = P.geom[leg][g];
+            const int lev = G.level;
+            v3 d = sel4(dB, lev);
+            float zc = (lev == 0 ? hk[0] : (lev == 1 ? hk[1] : (lev == 2 ? hk[2] : hk[3]))) + dot(d, ld3(G.pos));
+            v3 dl = tmul(ldm3(G.R), d);  // "up" in the mesh frame
+            float ext = fmaf(fabsf(dl.x), G.half[0], fmaf(fabsf(dl.y), G.half[1], fabsf(dl.z) * G.half[2]));
+            pass = zc - ext <= G.margin;  // oriented-box cull (conservative; same contacts as any cull)
+            e4 = make_float4(dl.x, dl.y, dl.z, zc);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (pass) {
+            const int pos = qn + __popc(m & lt);
+            wq.qd[pos] = e4;
+            wq.qmeta[pos] = leg | (g << 2);
+            if (pos < 32) { mine |= 1u << pos; gs |= (unsigned)g << (3 * nm); nm++; }
+            else { mine_next |= 1u << (pos - 32); gs_next |= (unsigned)g << (3 * nm_next); nm_next++; }
+        }
+        qn += __popc(m);
+        if (qn >= 32) {
+            run_batch(32);
+            collect(mine, gs);
+            // carry the overflow entries to the front of the queue
+            float4 cd = wq.qd[32 + lane];
+            int cmeta = wq.qmeta[32 + lane];
+            __syncwarp();
+            wq.qd[lane] = cd;
+            wq.qmeta[lane] = cmeta;
+            qn -= 32;
+            mine = mine_next; gs = gs_next; nm = nm_next;
+            mine_next = 0; gs_next = 0; nm_next = 0;
         }
     }
+    if (qn > 0) {
+        run_batch(qn);
+        collect(mine, gs);
+    }
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
 template <bool DEBUG, int CONE>
 DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const int* __restrict__ vert_adj,
                      const int4* __restrict__ adj4, const int* __restrict__ vert_cadj,
-                     const int4* __restrict__ cadj4, LaneState& S, int leg, const QuadRed& qr,
+                     const int4* __restrict__ cadj4, LaneState& S, int leg, const QuadRed& qr, const WarpQueue& wq,
                      int max_iter, int ls_iter, bool want_sensors, SensorOut& so, StepStats& st, Contacts& C,
                      const QgDebugOut& dbg, int env) {
     const float h = P.timestep;
@@ -437,7 +523,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
         }
     }
     C.n = 0;
-    collide_lane(P, verts, vert_adj, adj4, vert_cadj, cadj4, leg, fr, up, zb, C, st);
+    collide_lane(P, verts, vert_adj, adj4, vert_cadj, cadj4, leg, fr, up, zb, C, st, wq, qr.lane);
 #if QG_BLOCKSYNC >= 2
     __syncthreads();  // collision time varies per warp: re-align before the straight-line dynamics code
 #endif

@@ -45,5 +45,5 @@ for (f, l), a in agg.items():
     for j in range(3):
         b[k][j] += a[j]
 print("share_instr share_stall lanes  file:lines")
-for (f, l), a in sorted(b.items(), key=lambda kv: -kv[1][1])[:45]:
+for (f, l), a in sorted(b.items(), key=lambda kv: -kv[1][1])[:int(os.environ.get("NCU_TOP","45"))]:
     print(f"  {100*a[0]/te:5.1f}%  {100*a[1]/ts:5.1f}%  {a[2]/max(a[0],1):5.1f}  {f}:{l}-{l+9}")
