@@ -54,6 +54,7 @@ struct qg_batch {
     // environment binning (slot -> env permutation refreshed after every step launch)
     int *d_perm, *d_bin_count;   // d_bin_count: [2][QG_NBINS] = counts, cursors
     unsigned char* d_bin_key;
+    int* d_chunk;   // [2] chunk counter of the persistent step kernel, blocks-done counter
     bool perm_valid, binning;
     // device staging for the host-buffer path (qg_step_host)
     float *d_act, *d_obs, *d_rew;
@@ -512,10 +513,14 @@ extern "C" int qg_batch_create(const qg_model* m, int n_envs, int device, qg_bat
     CUDA_OK(cudaMalloc(&b->d_bin_count, sizeof(int) * 2 * QG_NBINS));
     CUDA_OK(cudaMalloc(&b->d_bin_key, n_envs));
     CUDA_OK(cudaMemset(b->d_bin_key, 0, n_envs));
+    CUDA_OK(cudaMalloc(&b->d_chunk, 2 * sizeof(int)));
+    CUDA_OK(cudaMemset(b->d_chunk, 0, 2 * sizeof(int)));
     b->perm_valid = false;
-    // opt-in experiment (QG_BINNING=1): measured +1 % at 65,536 envs under random actions (last-step solver effort is a
-    // weak predictor there), for 2 extra launches per step -- off by default
-    b->binning = false;
+    // environment binning (slot -> env permutation refreshed every step from the last physics step's per-leg contact count
+    // and Newton iterations): measured -2 % step time at 65,536 envs, for 2 extra tiny launches per step.  On by default
+    // only for batches large enough to pay for those; QG_BINNING=0/1 overrides.  Results per environment do not depend
+    // on the slot (test_env_binning_does_not_change_results).
+    b->binning = n_envs >= 32768;
     if (const char* ev = getenv("QG_BINNING")) b->binning = atoi(ev) != 0;   // tests / experiments
     b->smem = ((sizeof(QgModelC) + 15) & ~size_t(15)) + sizeof(float4) * nv + sizeof(float) * (QG_QR_SLOTS * 32 + QG_CQ_FLOATS) * (QG_BLOCK / 32);
     CUDA_OK(cudaFuncSetAttribute(qg_step_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
@@ -534,7 +539,7 @@ extern "C" void qg_batch_destroy(qg_batch* b) {
     if (!b) return;
     cudaSetDevice(b->device);
     cudaFree(b->d_model); cudaFree(b->d_verts); cudaFree(b->d_vert_adj); cudaFree(b->d_adj4); cudaFree(b->d_vert_cadj); cudaFree(b->d_cadj4);
-    cudaFree(b->d_state); cudaFree(b->d_ctr); cudaFree(b->d_perm); cudaFree(b->d_bin_count); cudaFree(b->d_bin_key);
+    cudaFree(b->d_state); cudaFree(b->d_ctr); cudaFree(b->d_perm); cudaFree(b->d_bin_count); cudaFree(b->d_bin_key); cudaFree(b->d_chunk);
     cudaFree(b->d_act); cudaFree(b->d_obs); cudaFree(b->d_rew); cudaFree(b->d_term);
     for (void* p : b->walk_allocs) cudaFree(p);
     delete b;
@@ -573,6 +578,8 @@ static inline int nblocks(int n_envs) { return (4 * n_envs + QG_BLOCK - 1) / QG_
 // one halving for small batches whose grid would leave SMs without a block
 static int step_block(const qg_batch* b) {
     int blk = QG_BLOCK;
+    static const int forced = getenv("QG_STEP_BLOCK") ? atoi(getenv("QG_STEP_BLOCK")) : 0;   // tuning experiments
+    if (forced >= 32 && forced <= QG_BLOCK && forced % 32 == 0) return forced;
     if (blk > 128 && (4 * b->n + blk - 1) / blk < b->num_sms) blk >>= 1;
     return blk;
 }
@@ -596,10 +603,12 @@ static int launch_step(qg_batch* b, const float* action, int clip, int frame_ski
                        unsigned char* terminated, float* terminal_obs, QgDebugOut dbg, cudaStream_t st) {
     const int blk = step_block(b);
     auto kern = b->cone ? qg_step_kernel<DEBUG, 1> : qg_step_kernel<DEBUG, 0>;
-    kern<<<(4 * b->n + blk - 1) / blk, blk, b->smem, st>>>(b->d_model, b->d_verts, b->d_vert_adj, b->d_adj4, b->d_vert_cadj, b->d_cadj4,
+    const int nchunks = (4 * b->n + blk - 1) / blk;
+    kern<<<nchunks < b->num_sms ? nchunks : b->num_sms, blk, b->smem, st>>>(b->d_model, b->d_verts, b->d_vert_adj, b->d_adj4, b->d_vert_cadj, b->d_cadj4,
                                                                      b->d_state, b->n, action, clip, frame_skip, obs, reward,
                                                                      terms, terminated, terminal_obs, b->opts, b->d_ctr, dbg,
-                                                                     b->perm_valid ? b->d_perm : nullptr, b->binning ? b->d_bin_key : nullptr);
+                                                                     b->perm_valid ? b->d_perm : nullptr, b->binning ? b->d_bin_key : nullptr,
+                                                                     b->d_chunk, nchunks);
     g_launches++;
     CUDA_OK(cudaGetLastError());
     if (b->binning) {   // next launch's slot -> env map: group environments by last-step solver effort

@@ -136,7 +136,7 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
                int clip_action, int frame_skip, float* __restrict__ obs, float* __restrict__ reward,
                float* __restrict__ terms, unsigned char* __restrict__ terminated, float* __restrict__ terminal_obs,
                QgStepOpts opts, QgCounters* __restrict__ ctr, QgDebugOut dbg, const int* __restrict__ perm,
-               unsigned char* __restrict__ bin_key) {
+               unsigned char* __restrict__ bin_key, int* __restrict__ chunk_ctr, int nchunks) {
     extern __shared__ __align__(16) unsigned char smem[];
     QgModelC& P = *reinterpret_cast<QgModelC*>(smem);
     float4* sverts = reinterpret_cast<float4*>(smem + ((sizeof(QgModelC) + 15) & ~size_t(15)));
@@ -150,8 +150,19 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
         int nv = gm->nvert;
         for (int i = threadIdx.x; i < nv; i += blockDim.x) sverts[i] = gverts[i];
     }
+    // Persistent blocks (one per SM): the model tables are staged once, then the block pulls chunks of
+    // blockDim.x / 4 environments from a device counter until the batch is done (dynamic: chunks differ in cost).
+    __shared__ int s_chunk;
+    const QgDebugOut dbg_in = dbg;
+#pragma unroll 1
+    for (;;) {
+    __syncthreads();   // staging done / previous chunk finished with s_chunk
+    if (threadIdx.x == 0) s_chunk = atomicAdd(chunk_ctr, 1);
     __syncthreads();
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int chunk = s_chunk;
+    if (chunk >= nchunks) break;
+    dbg = dbg_in;
+    const int t = chunk * blockDim.x + threadIdx.x;
     const int leg = t & 3;
     // quads past the end of the batch shadow the last environment (same reads, no writes) so that every thread
     // of the block reaches the same barriers
@@ -301,8 +312,9 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
         cv[9] = st.nact;
         }
         if (bin_key) {   // key of the next launch's binning: which legs were in contact, and the Newton iterations needed
-            int pattern = qsumi((C.n > 0 ? 1 : 0) << leg, qm);
-            if (leg == 0 && valid) bin_key[env] = (unsigned char)(min(st.last_iter, 3) * 16 + pattern);
+            int mnc = max(C.n, __shfl_xor_sync(qm, C.n, 1));
+            mnc = max(mnc, __shfl_xor_sync(qm, mnc, 2));
+            if (leg == 0 && valid) bin_key[env] = (unsigned char)(min(mnc, 7) * 8 + min(st.last_iter, 7));
         }
     }
 
@@ -316,6 +328,12 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
             for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
             if ((threadIdx.x & 31) == 0 && x) atomicAdd(out + i, x);
         }
+    }
+    }   // chunk loop
+    // the last block to leave re-arms the chunk counter for the next launch (no host-side state: graph-capture safe)
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(chunk_ctr + 1, 1) == (int)gridDim.x - 1) { chunk_ctr[0] = 0; chunk_ctr[1] = 0; }
     }
 }
 
@@ -420,8 +438,8 @@ __global__ void qg_ffma_kernel(float* out, int iters, float a, float b) {
 
 
 // ---------------------------------------------------------------------------------------------
-// Counting sort of the environments by the key the step kernel left (64 bins: Newton iterations x which legs were in
-// contact in the last physics step).  Two tiny launches per env.step(); the order inside a bin is irrelevant.
+// Counting sort of the environments by the key the step kernel left (64 bins: largest per-leg contact count x Newton
+// iterations of the last physics step -- the two trip counts a warp pays the maximum of).  Two tiny launches per env.step(); the order inside a bin is irrelevant.
 #define QG_NBINS 64
 __global__ void qg_bin_hist_kernel(const unsigned char* __restrict__ key, int N, int* __restrict__ count) {
     __shared__ int sc[QG_NBINS];

@@ -278,9 +278,8 @@ DI WarpQueue warp_queue(float* w) {
 }
 
 // pass 2 for one queue entry; returns the number of contacts written to out[0..3]
-DI int narrow_phase(const QgModelC& P, const float4* __restrict__ verts, const int* __restrict__ vert_adj,
-                    const int4* __restrict__ adj4, const int* __restrict__ vert_cadj, const int4* __restrict__ cadj4,
-                    float4 e4, int meta, float4* out, int& nvert) {
+DI int narrow_phase(const QgModelC& P, const float4* __restrict__ verts, const int4* __restrict__ adj4,
+                    const int4* __restrict__ cadj4, float4 e4, int meta, float4* out, int& nvert) {
     const QgGeomC& G = P.geom[meta & 3][meta >> 2];
     const v3 dl = V3(e4.x, e4.y, e4.z);
     const float zc = e4.w, margin = G.margin;
@@ -421,20 +420,13 @@ DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const 
             }
         }
     };
-    auto run_batch = [&](int n) {
-        __syncwarp();
-        if (lane < n) {
-            wq.rcnt[lane] = narrow_phase(P, verts, vert_adj, adj4, vert_cadj, cadj4, wq.qd[lane], wq.qmeta[lane],
-                                         wq.res + lane * 4, st.nvert);
-        }
-        __syncwarp();
-    };
     int qn = 0;                          // warp-uniform queue length
     unsigned mine = 0, mine_next = 0;    // this lane's entries: slots of the batch in flight / of the carry-over
     unsigned gs = 0, gs_next = 0;        // their geom ids, 3 bits each, in slot order
     int nm = 0, nm_next = 0;
+    // one more trip than there are geoms: the last one only drains the queue (ONE narrow-phase site in the code)
 #pragma unroll 1
-    for (int g = 0; g < ngmax; ++g) {
+    for (int g = 0; g <= ngmax; ++g) {
         bool pass = false;
         float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (g < ng) {
@@ -456,8 +448,13 @@ DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const 
             else { mine_next |= 1u << (pos - 32); gs_next |= (unsigned)g << (3 * nm_next); nm_next++; }
         }
         qn += __popc(m);
-        if (qn >= 32) {
-            run_batch(32);
+        if (qn >= 32 || (g == ngmax && qn > 0)) {
+            const int nb = min(qn, 32);
+            // pass 2: lane i takes queue entry i
+            __syncwarp();
+            if (lane < nb)
+                wq.rcnt[lane] = narrow_phase(P, verts, adj4, cadj4, wq.qd[lane], wq.qmeta[lane], wq.res + lane * 4, st.nvert);
+            __syncwarp();
             collect(mine, gs);
             // carry the overflow entries to the front of the queue
             float4 cd = wq.qd[32 + lane];
@@ -465,14 +462,10 @@ DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const 
             __syncwarp();
             wq.qd[lane] = cd;
             wq.qmeta[lane] = cmeta;
-            qn -= 32;
+            qn -= nb;
             mine = mine_next; gs = gs_next; nm = nm_next;
             mine_next = 0; gs_next = 0; nm_next = 0;
         }
-    }
-    if (qn > 0) {
-        run_batch(qn);
-        collect(mine, gs);
     }
     __syncwarp();
 }

@@ -36,6 +36,9 @@ hi = [i for i, r in enumerate(rows) if "Source" in r and any("Instructions Execu
 h = rows[hi]
 ce = h.index("Instructions Executed"); cs = [i for i, c in enumerate(h) if c.startswith("Warp Stall Sampling (All")][0]
 ct = [i for i, c in enumerate(h) if c.startswith("Thread Instructions Executed")][0]
+REASONS = ["stall_barrier", "stall_wait", "stall_short_sb", "stall_long_sb", "stall_branch_resolving", "stall_no_inst",
+           "stall_not_selected", "stall_selected", "stall_dispatch", "stall_math", "stall_mio", "stall_lg"]
+cr = [h.index(r) for r in REASONS]
 body = [r for r in rows[hi + 1:] if len(r) == len(h)]
 assert len(body) == len(lines), (len(body), len(lines))
 def _mark(txt):
@@ -55,6 +58,7 @@ _L = [(n, _mark(t)) for n, t in _M]
 REG = [(n, "qg_step.cuh", l, (_L[i + 1][1] if i + 1 < len(_L) else 100000)) for i, (n, l) in enumerate(_L)]
 REG.append(("kernel prologue/epilogue", "qg_kernels.cuh", 0, 100000))
 agg = collections.defaultdict(lambda: [0.0, 0.0, 0.0, 0])
+rs = collections.defaultdict(lambda: [0.0] * len(REASONS))
 for key, r in zip(lines, body):
     name = "other " + key[0]
     for n, f, a, b in REG:
@@ -62,8 +66,15 @@ for key, r in zip(lines, body):
             name = n; break
     x = agg[name]
     x[0] += float(r[ce] or 0); x[1] += float(r[cs] or 0); x[2] += float(r[ct] or 0); x[3] += 1
+    for j, c in enumerate(cr):
+        rs[name][j] += float(r[c] or 0)
 te = sum(a[0] for a in agg.values()); ts = sum(a[1] for a in agg.values())
 print(f"total warp-instr {te:.3e}; stall samples {ts:.0f}")
 print(f"{'region':28s} {'sass':>6s} {'instr%':>7s} {'time%':>7s} {'lanes':>6s}")
 for n, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{n:28s} {a[3]:6d} {100*a[0]/te:6.1f}% {100*a[1]/ts:6.1f}% {a[2]/max(a[0],1):6.1f}")
+print()
+print("stall mix per region (% of the region's samples): " + " ".join(r.replace("stall_", "")[:7] for r in REASONS))
+for n, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    t = max(sum(rs[n]), 1.0)
+    print(f"{n:28s} " + " ".join(f"{100 * v / t:7.0f}" for v in rs[n]))

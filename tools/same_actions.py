@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 from quadruped_gym_b200 import VecQuadrupedEnv
 from quadruped_gym_b200.envs import rewards as R
 n = 65536
-for mode in ("same", "random", "quad_same"):
+for mode in os.environ.get("MODES", "same,random,quad_same").split(","):
     env = VecQuadrupedEnv(n, "cuda:0", termination_fns={"flip": R.flip_termination()}, auto_reset=True)
     env.reset()
     g = torch.Generator(device="cuda"); g.manual_seed(0)
