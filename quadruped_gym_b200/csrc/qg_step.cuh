@@ -716,7 +716,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
 #pragma unroll
     for (int i = 0; i < 3; ++i) { rl[i] = fsl[i]; fcl[i] = 0.f; }
     int phase = 0, iter = 0, nact_last = 0;
-    float cost_old = 0.f, impr_est = 0.f;
+    float impr_est = 0.f;
     bool done = false;
 #pragma unroll 1
     for (;;) {
@@ -927,8 +927,8 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
 
         float gb[6], gl[3];
         if (nefc > 0) {
-            // ---- constraint update at the current point: forces, cost, J^T f, gradient
-            float cost = 0.f;
+            // ---- constraint update at the current point: forces, J^T f, gradient  (the cost value itself is not needed:
+            //      convergence uses the line-search model's decrease, see impr_est)
             v3 Fb = V3(0, 0, 0), Nb = V3(0, 0, 0);
             float tau[3] = {0.f, 0.f, 0.f};
             nact_last = 0;
@@ -940,14 +940,12 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                 v3 fc;
                 if (CONE) {
                     EllZ z = ell_eval(C.jar[0][c], C.jar[1][c], C.jar[2][c], mu, mus, D, D * impr);
-                    cost += z.cost;
                     nact_last += z.zone ? 3 : 0;
                     fc = fma3(z.f0, up, fma3(z.f1, ty, (-z.f2) * tx));   // rows: n = up, t1 = ty, t2 = -tx
                 } else {
                     float j0 = C.jar[0][c], j1 = C.jar[1][c], j2 = C.jar[2][c], j3 = C.jar[3][c];
                     float f0 = j0 < 0.f ? -D * j0 : 0.f, f1 = j1 < 0.f ? -D * j1 : 0.f;
                     float f2 = j2 < 0.f ? -D * j2 : 0.f, f3 = j3 < 0.f ? -D * j3 : 0.f;
-                    cost -= 0.5f * (f0 * j0 + f1 * j1 + f2 * j2 + f3 * j3);
                     nact_last += (j0 < 0.f) + (j1 < 0.f) + (j2 < 0.f) + (j3 < 0.f);
                     // force vector in B: sum f_k w_k,  w = up +- mu*ty, up -+ mu*tx
                     fc = fma3(f0 + f1 + f2 + f3, up, fma3(mu * (f0 - f1), ty, (-mu * (f2 - f3)) * tx));
@@ -964,16 +962,9 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                 if (lsgn[k] != 0.f && ljar[k] < 0.f) {
                     float f = -lD[k] * ljar[k];
                     nact_last++;
-                    cost -= 0.5f * f * ljar[k];
                     tau[k] += lsgn[k] * f;
                 }
             }
-            float gauss_l = 0.f, gauss_b = 0.f;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) gauss_l += 0.5f * (Mal[k] - fsl[k]) * (al[k] - a0l[k]);
-#pragma unroll
-            for (int r = 0; r < 6; ++r) gauss_b += 0.5f * (Mab[r] - fsb[r]) * (ab[r] - a0b[r]);
-            qr_put(qr, 0, cost + gauss_l);
             qr_put(qr, 1, Fb.x); qr_put(qr, 2, Fb.y); qr_put(qr, 3, Fb.z);
             qr_put(qr, 4, Nb.x); qr_put(qr, 5, Nb.y); qr_put(qr, 6, Nb.z);
             float g2 = 0.f, g2b = 0.f;
@@ -981,7 +972,6 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
             for (int k = 0; k < 3; ++k) { fcl[k] = tau[k]; gl[k] = Mal[k] - fsl[k] - tau[k]; g2 += gl[k] * gl[k]; }
             qr_put(qr, 7, g2);
             qr_sync(qr);
-            cost = qr_get(qr, 0) + gauss_b;
 #pragma unroll
             for (int r = 0; r < 6; ++r) fcb[r] = qr_get(qr, 1 + r);
             g2 = qr_get(qr, 7);
@@ -993,7 +983,6 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                 float improvement = P.scale * impr_est;
                 conv = improvement < P.tol || gradient < P.tol || iter >= max_iter;
             }
-            cost_old = cost;
         }
 
         if (conv) {
@@ -1054,21 +1043,19 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                 v3 jc0 = lev >= 1 ? sl[0] + cross(sa[0], xc) : V3(0, 0, 0);
                 v3 jc1 = lev >= 2 ? sl[1] + cross(sa[1], xc) : V3(0, 0, 0);
                 v3 jc2 = lev >= 3 ? sl[2] + cross(sa[2], xc) : V3(0, 0, 0);
-#define WMUL(v, out)                                                                             \
-    {                                                                                            \
-        float p0 = dot(up, v), p1 = dot(ty, v), p2 = -dot(tx, v);                                \
-        float c0 = w00 * p0 + w01 * p1 + w02 * p2, c1 = w01 * p0 + w11 * p1 + w12 * p2;          \
-        float c2 = w02 * p0 + w12 * p1 + w22 * p2;                                               \
-        out = fma3(c0, up, fma3(c1, ty, (-c2) * tx));                                            \
-    }
-                v3 Wx, Wy, Wz, q0, q1v, q2v;
-                WMUL(V3(1, 0, 0), Wx);
-                WMUL(V3(0, 1, 0), Wy);
-                WMUL(V3(0, 0, 1), Wz);
-                WMUL(jc0, q0);
-                WMUL(jc1, q1v);
-                WMUL(jc2, q2v);
-#undef WMUL
+                // stiffness in B coordinates, formed once: Wb = E^T W E = sum_i e_i g_i^T with g_i = sum_j W_ij e_j
+                v3 g0 = fma3(w00, up, fma3(w01, ty, (-w02) * tx));
+                v3 g1 = fma3(w01, up, fma3(w11, ty, (-w12) * tx));
+                v3 g2 = fma3(w02, up, fma3(w12, ty, (-w22) * tx));
+                s3 Wb;
+                Wb.xx = fmaf(up.x, g0.x, fmaf(ty.x, g1.x, -tx.x * g2.x));
+                Wb.yy = fmaf(up.y, g0.y, fmaf(ty.y, g1.y, -tx.y * g2.y));
+                Wb.zz = fmaf(up.z, g0.z, fmaf(ty.z, g1.z, -tx.z * g2.z));
+                Wb.xy = fmaf(up.x, g0.y, fmaf(ty.x, g1.y, -tx.x * g2.y));
+                Wb.xz = fmaf(up.x, g0.z, fmaf(ty.x, g1.z, -tx.x * g2.z));
+                Wb.yz = fmaf(up.y, g0.z, fmaf(ty.y, g1.z, -tx.y * g2.z));
+                const v3 Wx = V3(Wb.xx, Wb.xy, Wb.xz), Wy = V3(Wb.xy, Wb.yy, Wb.yz), Wz = V3(Wb.xz, Wb.yz, Wb.zz);
+                const v3 q0 = mul(Wb, jc0), q1v = mul(Wb, jc1), q2v = mul(Wb, jc2);
                 Hll[0] += dot(jc0, q0); Hll[1] += dot(jc0, q1v); Hll[2] += dot(jc0, q2v);
                 Hll[3] += dot(jc1, q1v); Hll[4] += dot(jc1, q2v); Hll[5] += dot(jc2, q2v);
                 v3 x0 = cross(xc, q0), x1 = cross(xc, q1v), x2 = cross(xc, q2v);
