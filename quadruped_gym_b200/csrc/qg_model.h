@@ -16,7 +16,9 @@
 #define QG_MAXVERT 1024     // unique hull vertices over all meshes (float4 each in shared memory)
 #define QG_MAX_TERMS_ 16
 #define QG_MAXMESH 8
+#ifndef QG_DIRRES
 #define QG_DIRRES 8          // support-search start table: cube map, 6 faces x QG_DIRRES^2 cells per mesh
+#endif
 #define QG_DIRCELLS (6 * QG_DIRRES * QG_DIRRES)
 
 // state planes: float4 S[plane * N + env]
