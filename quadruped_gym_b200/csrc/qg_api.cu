@@ -604,7 +604,8 @@ static int launch_step(qg_batch* b, const float* action, int clip, int frame_ski
     const int blk = step_block(b);
     auto kern = b->cone ? qg_step_kernel<DEBUG, 1> : qg_step_kernel<DEBUG, 0>;
     const int nchunks = (4 * b->n + blk - 1) / blk;
-    kern<<<nchunks < b->num_sms ? nchunks : b->num_sms, blk, b->smem, st>>>(b->d_model, b->d_verts, b->d_vert_adj, b->d_adj4, b->d_vert_cadj, b->d_cadj4,
+    const int resident = b->num_sms * (QG_BLOCK / blk);   // 255 registers: QG_BLOCK threads per SM
+    kern<<<nchunks < resident ? nchunks : resident, blk, b->smem, st>>>(b->d_model, b->d_verts, b->d_vert_adj, b->d_adj4, b->d_vert_cadj, b->d_cadj4,
                                                                      b->d_state, b->n, action, clip, frame_skip, obs, reward,
                                                                      terms, terminated, terminal_obs, b->opts, b->d_ctr, dbg,
                                                                      b->perm_valid ? b->d_perm : nullptr, b->binning ? b->d_bin_key : nullptr,

@@ -57,11 +57,11 @@ class VecPOWalkingQuadrupedEnv(VecWalkingQuadrupedEnv):
                                   int(self.auto_reset), st), "qg_walk_step")
         if self.auto_reset:
             _lib.check(L.qg_reset(self._batch, _ptr(self._terminated), self.seed_value, int(self.random_init), self.env_offset, st), "qg_reset")
-        terminated = self._terminated.bool()
-        self._last_sensordata = torch.where(terminated[:, None], self._term_obs, self._obs) if self.auto_reset else self._obs
+        terminated = self._terminated.view(torch.bool)
+        self._sd_pending, self._sd_merge = True, bool(self.auto_reset)
         self.info = {k: self._wterms[:, i] for i, k in enumerate(self.reward_keys)}
         self.info["terminal_observation"] = self._term_stacked
-        return self._stacked, self._reward, terminated, torch.zeros_like(terminated), self.info
+        return self._stacked, self._reward, terminated, self._truncated, self.info
 
 
 class SB3VecEnvAdapter:

@@ -112,7 +112,7 @@ class DataView:
 
     @property
     def sensordata(self):
-        return self._env._last_sensordata
+        return self._env._sensordata()
 
 
 class VecQuadrupedEnv:
@@ -156,7 +156,10 @@ class VecQuadrupedEnv:
         self._reward = torch.zeros((n,), dtype=torch.float32, device=dev)
         self._terminated = torch.zeros((n,), dtype=torch.uint8, device=dev)
         self._terms = torch.zeros((n, _lib.QG_MAX_TERMS), dtype=torch.float32, device=dev)
-        self._last_sensordata = torch.zeros((n, 33), dtype=torch.float32, device=dev)
+        self._truncated = torch.zeros((n,), dtype=torch.bool, device=dev)   # quadruped.py:179: never truncated
+        # env.data.sensordata is materialised on demand (no per-step kernel for a field few callers read)
+        self._sd = torch.zeros((n, 33), dtype=torch.float32, device=dev)
+        self._sd_pending, self._sd_merge = False, False
         self.data = DataView(self)
         # modular reward / termination dictionaries (quadruped.py:97-100)
         self.reward_fns: Dict[str, object] = reward_fns if reward_fns is not None else {"default": self._default_reward}
@@ -212,11 +215,22 @@ class VecQuadrupedEnv:
                                        self._stream()), "qg_reset")
         if m is None:
             self._obs.zero_()
-            self._last_sensordata.zero_()
+            self._sd, self._sd_pending = torch.zeros_like(self._obs), False
         else:
+            sd = self._sensordata()
+            self._sd, self._sd_pending = (sd.clone() if sd is self._obs else sd), False
             self._obs[m.bool()] = 0
-            self._last_sensordata[m.bool()] = 0
+            self._sd[m.bool()] = 0
         return self._obs, {}
+
+    def _sensordata(self) -> torch.Tensor:
+        """``data.sensordata``: sensordata of the last forward pass, also for environments that were auto-reset in the
+        same call (their returned observation is the reset observation).  Valid until the next ``step``."""
+        if self._sd_pending:
+            t = self._terminated.view(torch.bool)
+            self._sd = torch.where(t[:, None], self._term_obs, self._obs) if self._sd_merge else self._obs
+            self._sd_pending = False
+        return self._sd
 
     def step(self, action: torch.Tensor):
         self._sync_tables()
@@ -225,9 +239,8 @@ class VecQuadrupedEnv:
         _lib.check(_lib.lib().qg_step(self._batch, _ptr(a), self.frame_skip, _ptr(self._obs), _ptr(self._reward),
                                       _ptr(self._terms) if nterm else None, _ptr(self._terminated),
                                       _ptr(self._term_obs), self._stream()), "qg_step")
-        terminated = self._terminated.bool()
-        # env.data.sensordata = sensordata of the last forward pass, also for envs that were auto-reset
-        self._last_sensordata = torch.where(terminated[:, None], self._term_obs, self._obs) if self._kernel_reset else self._obs
+        terminated = self._terminated.view(torch.bool)   # 0/1 bytes: a view, no kernel
+        self._sd_pending, self._sd_merge = True, self._kernel_reset
         reward = self._reward
         info = {"reward_components": {}}
         if nterm:
@@ -246,8 +259,7 @@ class VecQuadrupedEnv:
                 self._term_obs = torch.where(terminated[:, None], self._obs, torch.zeros_like(self._obs))
                 self.reset(mask=terminated)
         info["terminal_observation"] = self._term_obs
-        truncated = torch.zeros_like(terminated)  # quadruped.py:179
-        return self._obs, reward, terminated, truncated, info
+        return self._obs, reward, terminated, self._truncated, info
 
     def pinned_action_buffer(self) -> np.ndarray:
         """A page-locked [N,12] float32 array: fill it and pass it to ``step_host`` for a staging-free H2D copy."""
