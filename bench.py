@@ -28,6 +28,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+NPOOL = int(os.environ.get("QG_BENCH_NPOOL", "64"))   # independent random action tensors cycled through (period 64 steps = 0.5 s of simulated time)
 PREROLL = 100   # untimed env steps before the warm-up (robots have landed and stumble under random actions)
 METRIC = "env-steps/sec (physics steps incl. frame_skip)"
 UNIT = "physics env-steps/s"
@@ -217,7 +218,7 @@ def run_ours(a):
         env.set_state(qpos=q)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    pool = [torch.rand((envs, 12), device=dev, generator=gen) * 2 - 1 for _ in range(8)]  # resident in HBM
+    pool = [torch.rand((envs, 12), device=dev, generator=gen) * 2 - 1 for _ in range(NPOOL)]  # resident in HBM
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -229,9 +230,9 @@ def run_ours(a):
     # untimed pre-roll into the steady state: every episode starts with a ~0.1 m drop (28 contact-free env steps), so
     # without it a short run would time free-fall instead of the contact-rich rollout the metric is about
     for i in range(PREROLL):
-        env.step(pool[i % 8])
+        env.step(pool[i % NPOOL])
     for i in range(max(a.warmup, 3)):
-        env.step(pool[i % 8])
+        env.step(pool[i % NPOOL])
     barrier()
     env.counters(reset=True)
     launches0 = _lib.lib().qg_launch_count()
@@ -246,10 +247,10 @@ def run_ours(a):
     for i in range(a.steps):
         flush.fill_(float(i))  # evict the state planes from L2 between timed steps
         ev[i][0].record()
-        o, r, te, _, _ = env.step(pool[i % 8])
+        o, r, te, _, _ = env.step(pool[i % NPOOL])
         if rollout is not None:
             t = i % 24
-            rollout["obs"][t].copy_(o); rollout["act"][t].copy_(pool[i % 8]); rollout["rew"][t].copy_(r); rollout["done"][t].copy_(te)
+            rollout["obs"][t].copy_(o); rollout["act"][t].copy_(pool[i % NPOOL]); rollout["rew"][t].copy_(r); rollout["done"][t].copy_(te)
         ev[i][1].record()
     barrier()
     t1 = time.perf_counter()
@@ -264,11 +265,11 @@ def run_ours(a):
         hpool_t = [p.cpu().pin_memory() for p in pool]   # this step's inputs live in pinned host memory
         hpool = [t.numpy() for t in hpool_t]
         for i in range(3):
-            env.step_host(hpool[i % 8])
+            env.step_host(hpool[i % NPOOL])
         barrier()
         te0 = time.perf_counter()
         for i in range(a.steps):
-            env.step_host(hpool[i % 8])
+            env.step_host(hpool[i % NPOOL])
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - te0
         barrier()
@@ -311,7 +312,7 @@ def run_ours(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "envs_per_gpu": envs, "frame_skip": fs, "actions": "U(-1,1)^12 resident in HBM, 8 tensors cycled",
+            "config": {"workload": desc, "envs_per_gpu": envs, "frame_skip": fs, "actions": "U(-1,1)^12 resident in HBM, %d tensors cycled" % NPOOL,
                        "l2": "flushed (256 MiB write) between timed steps", "preroll_steps": PREROLL, "rewards": "forward(qvel_x) - 0.1*sum(ctrl^2) + alive",
                        "parallelism": f"env-sharded x{world}, no data-path collective"},
             "clocks": clocks,
