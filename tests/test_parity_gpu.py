@@ -579,6 +579,35 @@ def test_env_binning_does_not_change_results(Vec, monkeypatch):
             assert torch.equal(x, y)
 
 
+def test_step_replays_from_a_cuda_graph(Vec, monkeypatch):
+    """qg_step keeps no host-side state per launch (the persistent kernel's chunk counter is re-armed on the device by the
+    last block to leave), so a captured launch can be replayed: graph replays and eager calls give identical bits.
+    Also covers more chunks than SMs (4,800 envs = 75 chunks of 64 on 148 SMs is not enough: use 12,800 = 200)."""
+    monkeypatch.setenv("QG_BINNING", "1")
+    n = 12800
+    rng = np.random.default_rng(5)
+    acts = [torch.from_numpy(rng.uniform(-1, 1, (n, 12)).astype(np.float32)).cuda() for _ in range(6)]
+    envs = [Vec(n, "cuda:0", auto_reset=True, max_time=0.5) for _ in range(2)]
+    for e in envs:
+        e.reset()
+        for t in range(30):   # land first; the binning permutation exists after the first step
+            e.step(acts[t % 6])
+    a_static = acts[0].clone()
+    g = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        envs[0].step(a_static)
+    for t in range(12):
+        a_static.copy_(acts[t % 6])
+        g.replay()
+        o1, r1, te1 = envs[0]._obs.clone(), envs[0]._reward.clone(), envs[0]._terminated.clone()
+        o2, r2, te2, _, _ = envs[1].step(acts[t % 6])
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(te1.bool(), te2)
+    assert torch.equal(envs[0].data.qpos, envs[1].data.qpos)
+    for e in envs:
+        e.close()
+
+
 def test_full_size_properties_and_rollout_buffer(Vec):
     """BASELINE sizes (65,536 envs): size-independent properties -- identical environments stay bit-identical under
     identical actions, every value stays finite, counters add up, and the [T,N,.] rollout buffer of config 4 fills on
