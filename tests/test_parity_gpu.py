@@ -638,7 +638,7 @@ def test_full_size_properties_and_rollout_buffer(Vec):
     env.close()
 
 
-@pytest.mark.parametrize("n", [1, 3, 63, 65, 1000])
+@pytest.mark.parametrize("n", [1, 3, 63, 65, 1000, 148 * 64 + 1])   # the last: one chunk more than persistent blocks
 def test_ragged_batch_sizes_and_state_roundtrip(Vec, oracle_model, n):
     """Batch sizes that do not fill a quad-of-quads / warp / block: tail quads must not disturb their neighbours,
     get_state(set_state(x)) == x, masked reset touches only the masked environments."""
