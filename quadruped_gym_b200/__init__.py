@@ -8,13 +8,23 @@ this package is the thin Python host: model compiler, ctypes binding, env classe
 from . import _lib  # noqa: F401
 from .model import compile_mjcf, load_model_blob  # noqa: F401
 
-__all__ = ["VecQuadrupedEnv", "QuadrupedEnv", "rewards", "compile_mjcf", "load_model_blob"]
+__all__ = ["VecQuadrupedEnv", "QuadrupedEnv", "VecWalkingQuadrupedEnv", "VecPOWalkingQuadrupedEnv", "SB3VecEnvAdapter",
+           "RolloutBuffer", "rewards", "compile_mjcf", "load_model_blob"]
 
 
 def __getattr__(name):  # torch is imported lazily so that the model compiler works without it
     if name in ("VecQuadrupedEnv", "QuadrupedEnv"):
         from .envs import quadruped
         return getattr(quadruped, name)
+    if name == "VecWalkingQuadrupedEnv":
+        from .envs import walking_quad
+        return walking_quad.VecWalkingQuadrupedEnv
+    if name in ("VecPOWalkingQuadrupedEnv", "SB3VecEnvAdapter"):
+        from .envs import po_walking_quad
+        return getattr(po_walking_quad, name)
+    if name == "RolloutBuffer":
+        from .rollout import RolloutBuffer
+        return RolloutBuffer
     if name == "rewards":
         from .envs import rewards
         return rewards

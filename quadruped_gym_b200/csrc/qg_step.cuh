@@ -261,6 +261,7 @@ __device__ __noinline__ float2 sincos_ni(float x) {
 // so results do not depend on the balancing.
 // `fr` holds the lane's 4 link frames (level 0 = base): rotation (row major, link -> B) and position.
 #define QG_CQ_CAP 64                                   // queue entries per warp (32 carried over + 32 pushed)
+static_assert(QG_MAXGEOM_LANE <= 8, "collide_lane packs a lane's geom ids of one batch in 3 bits each");
 #define QG_CQ_FLOATS (QG_CQ_CAP * 5 + 32 * 17)         // queue: float4 + meta; results: 4 float4 + count per slot
 struct WarpQueue {
     float4* qd;    // [QG_CQ_CAP] (dl.x, dl.y, dl.z, zc)
