@@ -33,7 +33,7 @@ static int fail(int code, const char* fmt, ...) {
 struct qg_model {
     QgModelC c;
     std::vector<float> verts;     // xyz_ per hull vertex
-    std::vector<int> vert_adj;    // per vertex: start of its neighbour list in int4 units, relative to the mesh' edge0
+    std::vector<int> vert_adj;    // per vertex: start of its neighbour list in int4 units, relative to the mesh' edge0 (rides in verts[].w)
     std::vector<int> adj;         // neighbour lists (local vertex ids), -1 terminated and padded to groups of 4
     std::vector<int> vert_cadj, cadj;  // same for the polytope-edge graph (hill climbing)
     int sizes[8];
@@ -44,7 +44,6 @@ struct qg_batch {
     int n, device;
     QgModelC* d_model;
     float4* d_verts;
-    int *d_vert_adj, *d_vert_cadj;
     int4 *d_adj4, *d_cadj4;
     float4* d_state;
     QgCounters* d_ctr;
@@ -495,17 +494,13 @@ extern "C" int qg_batch_create(const qg_model* m, int n_envs, int device, qg_bat
     size_t nv = m->verts.size() / 4;
     CUDA_OK(cudaMalloc(&b->d_model, sizeof(QgModelC)));
     CUDA_OK(cudaMalloc(&b->d_verts, sizeof(float4) * (nv ? nv : 1)));
-    CUDA_OK(cudaMalloc(&b->d_vert_adj, sizeof(int) * (nv ? nv : 1)));
     CUDA_OK(cudaMalloc(&b->d_adj4, sizeof(int) * (m->adj.size() ? m->adj.size() : 4)));
-    CUDA_OK(cudaMalloc(&b->d_vert_cadj, sizeof(int) * (nv ? nv : 1)));
     CUDA_OK(cudaMalloc(&b->d_cadj4, sizeof(int) * (m->cadj.size() ? m->cadj.size() : 4)));
     CUDA_OK(cudaMalloc(&b->d_state, sizeof(float4) * (size_t)QG_NPLANE * n_envs));
     CUDA_OK(cudaMalloc(&b->d_ctr, sizeof(QgCounters)));
     CUDA_OK(cudaMemcpy(b->d_model, &m->c, sizeof(QgModelC), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(b->d_verts, m->verts.data(), sizeof(float) * m->verts.size(), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(b->d_vert_adj, m->vert_adj.data(), sizeof(int) * m->vert_adj.size(), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(b->d_adj4, m->adj.data(), sizeof(int) * m->adj.size(), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(b->d_vert_cadj, m->vert_cadj.data(), sizeof(int) * m->vert_cadj.size(), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(b->d_cadj4, m->cadj.data(), sizeof(int) * m->cadj.size(), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemset(b->d_state, 0, sizeof(float4) * (size_t)QG_NPLANE * n_envs));
     CUDA_OK(cudaMemset(b->d_ctr, 0, sizeof(QgCounters)));
@@ -522,11 +517,16 @@ extern "C" int qg_batch_create(const qg_model* m, int n_envs, int device, qg_bat
     // on the slot (test_env_binning_does_not_change_results).
     b->binning = n_envs >= 32768;
     if (const char* ev = getenv("QG_BINNING")) b->binning = atoi(ev) != 0;   // tests / experiments
-    b->smem = ((sizeof(QgModelC) + 15) & ~size_t(15)) + sizeof(float4) * nv + sizeof(float) * (QG_QR_SLOTS * 32 + QG_CQ_FLOATS) * (QG_BLOCK / 32);
+    b->smem = ((sizeof(QgModelC) + 15) & ~size_t(15)) + sizeof(float4) * nv + sizeof(float) * (QG_QR_SLOTS * 32) * (QG_BLOCK / 32);
     CUDA_OK(cudaFuncSetAttribute(qg_step_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
     CUDA_OK(cudaFuncSetAttribute(qg_step_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
     CUDA_OK(cudaFuncSetAttribute(qg_step_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
     CUDA_OK(cudaFuncSetAttribute(qg_step_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+    if (const char* ev = getenv("QG_CARVEOUT")) {   // tuning experiments: shared-memory carve-out in percent
+        int pct = atoi(ev);
+        cudaFuncSetAttribute(qg_step_kernel<false, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(qg_step_kernel<false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
     b->cone = m->c.cone;
     *out = b;
     int rc = qg_reset(b, nullptr, 0, 0, 0, nullptr);
@@ -538,7 +538,7 @@ extern "C" int qg_batch_create(const qg_model* m, int n_envs, int device, qg_bat
 extern "C" void qg_batch_destroy(qg_batch* b) {
     if (!b) return;
     cudaSetDevice(b->device);
-    cudaFree(b->d_model); cudaFree(b->d_verts); cudaFree(b->d_vert_adj); cudaFree(b->d_adj4); cudaFree(b->d_vert_cadj); cudaFree(b->d_cadj4);
+    cudaFree(b->d_model); cudaFree(b->d_verts); cudaFree(b->d_adj4); cudaFree(b->d_cadj4);
     cudaFree(b->d_state); cudaFree(b->d_ctr); cudaFree(b->d_perm); cudaFree(b->d_bin_count); cudaFree(b->d_bin_key); cudaFree(b->d_chunk);
     cudaFree(b->d_act); cudaFree(b->d_obs); cudaFree(b->d_rew); cudaFree(b->d_term);
     for (void* p : b->walk_allocs) cudaFree(p);
@@ -605,7 +605,7 @@ static int launch_step(qg_batch* b, const float* action, int clip, int frame_ski
     auto kern = b->cone ? qg_step_kernel<DEBUG, 1> : qg_step_kernel<DEBUG, 0>;
     const int nchunks = (4 * b->n + blk - 1) / blk;
     const int resident = b->num_sms * (QG_BLOCK / blk);   // 255 registers: QG_BLOCK threads per SM
-    kern<<<nchunks < resident ? nchunks : resident, blk, b->smem, st>>>(b->d_model, b->d_verts, b->d_vert_adj, b->d_adj4, b->d_vert_cadj, b->d_cadj4,
+    kern<<<nchunks < resident ? nchunks : resident, blk, b->smem, st>>>(b->d_model, b->d_verts, b->d_adj4, b->d_cadj4,
                                                                      b->d_state, b->n, action, clip, frame_skip, obs, reward,
                                                                      terms, terminated, terminal_obs, b->opts, b->d_ctr, dbg,
                                                                      b->perm_valid ? b->d_perm : nullptr, b->binning ? b->d_bin_key : nullptr,

@@ -131,8 +131,8 @@ DI double np_sum12(const double* v) {
 
 template <bool DEBUG, int CONE>
 __global__ void __launch_bounds__(QG_BLOCK, QG_MINBLOCKS)
-qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gverts, const int* __restrict__ vert_adj,
-               const int4* __restrict__ adj4, const int* __restrict__ vert_cadj, const int4* __restrict__ cadj4, float4* __restrict__ S, int N, const float* __restrict__ action,
+qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gverts, const int4* __restrict__ adj4,
+               const int4* __restrict__ cadj4, float4* __restrict__ S, int N, const float* __restrict__ action,
                int clip_action, int frame_skip, float* __restrict__ obs, float* __restrict__ reward,
                float* __restrict__ terms, unsigned char* __restrict__ terminated, float* __restrict__ terminal_obs,
                QgStepOpts opts, QgCounters* __restrict__ ctr, QgDebugOut dbg, const int* __restrict__ perm,
@@ -141,8 +141,12 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
     QgModelC& P = *reinterpret_cast<QgModelC*>(smem);
     float4* sverts = reinterpret_cast<float4*>(smem + ((sizeof(QgModelC) + 15) & ~size_t(15)));
     // per-warp scratch of the quad all-reduce, behind the vertex table
-    float* sred = reinterpret_cast<float*>(sverts + gm->nvert) + (threadIdx.x >> 5) * (QG_QR_SLOTS * 32 + QG_CQ_FLOATS);
-    const WarpQueue wq = warp_queue(sred + QG_QR_SLOTS * 32);   // collision queue of this warp, behind its reduction rows
+    static_assert(QG_CQ_FLOATS <= QG_QR_SLOTS * 32, "the collision queue aliases the reduction rows");
+    float* sred = reinterpret_cast<float*>(sverts + gm->nvert) + (threadIdx.x >> 5) * (QG_QR_SLOTS * 32);
+    // The collision queue of this warp ALIASES its reduction rows: the two are never live together (block barriers
+    // separate the collision phase from the reductions before and after it), and 27 KB less shared memory per block is
+    // 27 KB more L1 for the thread-local contact tables and link frames.
+    const WarpQueue wq = warp_queue(sred);
     {
         const int4* src = reinterpret_cast<const int4*>(gm);
         int4* dst = reinterpret_cast<int4*>(smem);
@@ -211,7 +215,7 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
                 L.ctrl[0] = c0; L.ctrl[1] = c1; L.ctrl[2] = c2;
                 diverged += (leg == 0);
             }
-            physics_step<DEBUG, CONE>(P, sverts, vert_adj, adj4, vert_cadj, cadj4, L, leg, qr, wq, max_iter, ls_iter, s == frame_skip - 1, so,
+            physics_step<DEBUG, CONE>(P, sverts, adj4, cadj4, L, leg, qr, wq, max_iter, ls_iter, s == frame_skip - 1, so,
                                 st, C, dbg, env);
         }
 

@@ -371,10 +371,10 @@ DI int narrow_phase(const QgModelC& P, const float4* __restrict__ verts, const i
     return nout;
 }
 
-DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const int* __restrict__ vert_adj,
-                     const int4* __restrict__ adj4, const int* __restrict__ vert_cadj,
+DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const int4* __restrict__ adj4,
                      const int4* __restrict__ cadj4, int leg, const float* fr, v3 up, float zb, Contacts& C,
                      StepStats& st, const WarpQueue& wq, int lane) {
+    __syncwarp();   // the queue aliases the quad-reduction rows: every quad of the warp is done with them
     const int ng = P.ngeom[leg];
     const int ngmax = max(max(P.ngeom[0], P.ngeom[1]), max(P.ngeom[2], P.ngeom[3]));
     const unsigned lt = (1u << lane) - 1u;
@@ -473,8 +473,7 @@ DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const 
 
 // ---------------------------------------------------------------------------------------------
 template <bool DEBUG, int CONE>
-DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const int* __restrict__ vert_adj,
-                     const int4* __restrict__ adj4, const int* __restrict__ vert_cadj,
+DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const int4* __restrict__ adj4,
                      const int4* __restrict__ cadj4, LaneState& S, int leg, const QuadRed& qr, const WarpQueue& wq,
                      int max_iter, int ls_iter, bool want_sensors, SensorOut& so, StepStats& st, Contacts& C,
                      const QgDebugOut& dbg, int env) {
@@ -517,7 +516,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
         }
     }
     C.n = 0;
-    collide_lane(P, verts, vert_adj, adj4, vert_cadj, cadj4, leg, fr, up, zb, C, st, wq, qr.lane);
+    collide_lane(P, verts, adj4, cadj4, leg, fr, up, zb, C, st, wq, qr.lane);
 #if QG_BLOCKSYNC >= 2
     __syncthreads();  // collision time varies per warp: re-align before the straight-line dynamics code
 #endif
