@@ -398,8 +398,14 @@ DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const 
             if (n == 0) continue;
             const QgGeomC& G = P.geom[leg][g];
             const int lev = G.level;
-            m3 Rk = ldm3(fr + 12 * lev);
-            v3 ctr = ld3(fr + 12 * lev + 9) + mul(Rk, ld3(G.pos));
+            // static indices only: `fr` stays scalarised (registers / compiler-chosen spills) instead of a local array
+            m3 Rk;
+            v3 pk;
+            if (lev == 0) { Rk = ldm3(fr); pk = ld3(fr + 9); }
+            else if (lev == 1) { Rk = ldm3(fr + 12); pk = ld3(fr + 21); }
+            else if (lev == 2) { Rk = ldm3(fr + 24); pk = ld3(fr + 33); }
+            else { Rk = ldm3(fr + 36); pk = ld3(fr + 45); }
+            v3 ctr = pk + mul(Rk, ld3(G.pos));
             m3 RB = matmul(Rk, ldm3(G.R));  // mesh frame -> B
 #pragma unroll 1
             for (int k = 0; k < n; ++k) {
