@@ -44,14 +44,17 @@ struct StepStats {
     int last_nefc, last_iter;   // of the most recent physics step (env totals): the binning key of the next launch
 };
 
-// per-lane contact table (thread-local memory; only the first `nc` slots are ever touched)
+// per-lane contact table (thread-local memory; only the first `nc` slots are ever touched).  Four float4 per contact
+// so that every access is one 128-bit local load / store instead of four 32-bit ones.
 struct Contacts {
-    float x[QG_MAXCON_LANE], y[QG_MAXCON_LANE], z[QG_MAXCON_LANE];
-    float D[QG_MAXCON_LANE], mu[QG_MAXCON_LANE], Bd[QG_MAXCON_LANE], Kr[QG_MAXCON_LANE];
-    float jar[4][QG_MAXCON_LANE], jv[4][QG_MAXCON_LANE];
-    int lev[QG_MAXCON_LANE];
+    float4 geo[QG_MAXCON_LANE];   // contact point x, y, z (base frame) and the row stiffness D
+    float4 par[QG_MAXCON_LANE];   // mu, reference-acceleration damping B, K * imp * r, link level (int bits)
+    float4 jar[QG_MAXCON_LANE];   // J a - aref of the contact's rows (3 used with the elliptic cone)
+    float4 jv[QG_MAXCON_LANE];    // J v of the current search direction
     int n;
 };
+DI void ld4(float4 v, float* o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+DI float4 st4(const float* o) { return make_float4(o[0], o[1], o[2], o[3]); }
 
 __device__ __noinline__ float impedance(float r, float d0, float dmax, float width, float mid, float power) {
     float x = fabsf(r) / fmaxf(1e-15f, width), y;
@@ -417,12 +420,8 @@ DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const 
                     v3 xc = fma3(-0.5f * dv, up, xv);
                     float r = dv - G.margin;
                     float imp = impedance(r, G.d0, G.dmax, G.width, G.mid, G.power);
-                    C.x[c] = xc.x; C.y[c] = xc.y; C.z[c] = xc.z;
-                    C.D[c] = 1.f / fmaxf(1e-15f, (1.f - imp) / imp * G.Rfac);
-                    C.mu[c] = G.mu;
-                    C.Bd[c] = G.B;
-                    C.Kr[c] = G.K * imp * r;
-                    C.lev[c] = lev;
+                    C.geo[c] = make_float4(xc.x, xc.y, xc.z, 1.f / fmaxf(1e-15f, (1.f - imp) / imp * G.Rfac));
+                    C.par[c] = make_float4(G.mu, G.B, G.K * imp * r, __int_as_float(lev));
                 } else st.overflow++;
             }
         }
@@ -693,12 +692,14 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
     }
 #pragma unroll 1
     for (int c = 0; c < nc; ++c) {
-        v3 xc = V3(C.x[c], C.y[c], C.z[c]);
-        int lev = C.lev[c];
-        float rv[4];
-        contact_rows<CONE>(sel4(U, lev) + cross(sel4(W, lev), xc), tx, ty, up, C.mu[c], rv);
+        const float4 g4 = C.geo[c], p4 = C.par[c];
+        v3 xc = V3(g4.x, g4.y, g4.z);
+        int lev = __float_as_int(p4.w);
+        float rv[4], jr[4] = {0.f, 0.f, 0.f, 0.f};
+        contact_rows<CONE>(sel4(U, lev) + cross(sel4(W, lev), xc), tx, ty, up, p4.x, rv);
 #pragma unroll
-        for (int k = 0; k < NR; ++k) C.jar[k][c] = fmaf(C.Bd[c], rv[k], (CONE && k > 0) ? 0.f : C.Kr[c]);  // = -aref_k
+        for (int k = 0; k < NR; ++k) jr[k] = fmaf(p4.y, rv[k], (CONE && k > 0) ? 0.f : p4.z);  // = -aref_k
+        C.jar[c] = st4(jr);
     }
     qr_put(qr, 0, (float)(NR * nc + nlim));
     qr_sync(qr);
@@ -760,26 +761,29 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                 twist(a0b, a0l, sl, sa, U2, W2);
 #pragma unroll 1
                 for (int c = 0; c < nc; ++c) {
-                    v3 xc = V3(C.x[c], C.y[c], C.z[c]);
-                    int lev = C.lev[c];
-                    float rw[4], rs[4], D = C.D[c];
-                    contact_rows<CONE>(sel4(U, lev) + cross(sel4(W, lev), xc), tx, ty, up, C.mu[c], rw);
-                    contact_rows<CONE>(sel4(U2, lev) + cross(sel4(W2, lev), xc), tx, ty, up, C.mu[c], rs);
+                    const float4 g4 = C.geo[c], p4 = C.par[c];
+                    v3 xc = V3(g4.x, g4.y, g4.z);
+                    int lev = __float_as_int(p4.w);
+                    float rw[4], rs[4], jb[4], D = g4.w;
+                    ld4(C.jar[c], jb);
+                    contact_rows<CONE>(sel4(U, lev) + cross(sel4(W, lev), xc), tx, ty, up, p4.x, rw);
+                    contact_rows<CONE>(sel4(U2, lev) + cross(sel4(W2, lev), xc), tx, ty, up, p4.x, rs);
+                    if (CONE) { rw[3] = 0.f; rs[3] = 0.f; }
 #pragma unroll
                     for (int k = 0; k < NR; ++k) {
-                        float base = C.jar[k][c];
+                        float base = jb[k];
                         float jw = rw[k] + base, js = rs[k] + base;
                         rw[k] = jw; rs[k] = js;
-                        C.jar[k][c] = jw;
-                        C.jv[k][c] = js;
                         if (!CONE) {
                             cw += (jw < 0.f) ? 0.5f * D * jw * jw : 0.f;
                             cs += (js < 0.f) ? 0.5f * D * js * js : 0.f;
                         }
                     }
+                    C.jar[c] = st4(rw);   // at the warm start
+                    C.jv[c] = st4(rs);    // at qacc_smooth (parked here until the cheaper point is known)
                     if (CONE) {
-                        cw += ell_eval(rw[0], rw[1], rw[2], C.mu[c], mus, D, D * impr).cost;
-                        cs += ell_eval(rs[0], rs[1], rs[2], C.mu[c], mus, D, D * impr).cost;
+                        cw += ell_eval(rw[0], rw[1], rw[2], p4.x, mus, D, D * impr).cost;
+                        cs += ell_eval(rs[0], rs[1], rs[2], p4.x, mus, D, D * impr).cost;
                     }
                 }
                 float ljs[3];
@@ -809,9 +813,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                     for (int i = 0; i < 3; ++i) { al[i] = S.wj[i]; Mal[i] = Mwl[i]; }
                 } else {
 #pragma unroll 1
-                    for (int c = 0; c < nc; ++c)
-#pragma unroll
-                        for (int k = 0; k < NR; ++k) C.jar[k][c] = C.jv[k][c];
+                    for (int c = 0; c < nc; ++c) C.jar[c] = C.jv[c];
 #pragma unroll
                     for (int k = 0; k < 3; ++k) ljar[k] = ljs[k];
                 }
@@ -831,21 +833,22 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
             int flips = 0;
 #pragma unroll 1
             for (int c = 0; c < nc; ++c) {
-                v3 xc = V3(C.x[c], C.y[c], C.z[c]);
-                int lev = C.lev[c];
-                float rv[4], D = C.D[c];
-                contact_rows<CONE>(sel4(U, lev) + cross(sel4(W, lev), xc), tx, ty, up, C.mu[c], rv);
+                const float4 g4 = C.geo[c], p4 = C.par[c];
+                v3 xc = V3(g4.x, g4.y, g4.z);
+                int lev = __float_as_int(p4.w);
+                float rv[4], jb[4], D = g4.w;
+                ld4(C.jar[c], jb);
+                contact_rows<CONE>(sel4(U, lev) + cross(sel4(W, lev), xc), tx, ty, up, p4.x, rv);
+                C.jv[c] = st4(rv);
                 if (CONE) {
-                    float a0 = C.jar[0][c], a1 = C.jar[1][c], a2 = C.jar[2][c];
-                    C.jv[0][c] = rv[0]; C.jv[1][c] = rv[1]; C.jv[2][c] = rv[2];
-                    int zo0 = ell_ls_acc(a0, a1, a2, rv[0], rv[1], rv[2], C.mu[c], mus, D, D * impr, z1, z2);
-                    int zo1 = ell_ls_acc(a0 + rv[0], a1 + rv[1], a2 + rv[2], rv[0], rv[1], rv[2], C.mu[c], mus, D, D * impr, e1, e2);
+                    float a0 = jb[0], a1 = jb[1], a2 = jb[2];
+                    int zo0 = ell_ls_acc(a0, a1, a2, rv[0], rv[1], rv[2], p4.x, mus, D, D * impr, z1, z2);
+                    int zo1 = ell_ls_acc(a0 + rv[0], a1 + rv[1], a2 + rv[2], rv[0], rv[1], rv[2], p4.x, mus, D, D * impr, e1, e2);
                     flips += (zo0 != zo1 || zo0 == 2) ? 1 : 0;   // the cone surface is not quadratic: iterate
                 } else {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        float jv = rv[k], j0 = C.jar[k][c], j1 = j0 + jv;
-                        C.jv[k][c] = jv;
+                        float jv = rv[k], j0 = jb[k], j1 = j0 + jv;
                         if (j0 < 0.f) { z1 = fmaf(D * jv, j0, z1); z2 = fmaf(D * jv, jv, z2); }
                         if (j1 < 0.f) { e1 = fmaf(D * jv, j1, e1); e2 = fmaf(D * jv, jv, e2); }
                         flips += ((j0 < 0.f) != (j1 < 0.f)) ? 1 : 0;
@@ -888,15 +891,18 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                         e1 = 0.f; e2 = 0.f;
 #pragma unroll 1
                         for (int c = 0; c < nc; ++c) {
-                            float D = C.D[c];
+                            const float D = C.geo[c].w;
+                            float jb[4], vb[4];
+                            ld4(C.jar[c], jb);
+                            ld4(C.jv[c], vb);
                             if (CONE) {
-                                float v0 = C.jv[0][c], v1 = C.jv[1][c], v2 = C.jv[2][c];
-                                ell_ls_acc(fmaf(alpha, v0, C.jar[0][c]), fmaf(alpha, v1, C.jar[1][c]), fmaf(alpha, v2, C.jar[2][c]),
-                                           v0, v1, v2, C.mu[c], mus, D, D * impr, e1, e2);
+                                float v0 = vb[0], v1 = vb[1], v2 = vb[2];
+                                ell_ls_acc(fmaf(alpha, v0, jb[0]), fmaf(alpha, v1, jb[1]), fmaf(alpha, v2, jb[2]),
+                                           v0, v1, v2, C.par[c].x, mus, D, D * impr, e1, e2);
                             } else {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
-                                    float jv = C.jv[k][c], xx = fmaf(alpha, jv, C.jar[k][c]);
+                                    float jv = vb[k], xx = fmaf(alpha, jv, jb[k]);
                                     if (xx < 0.f) { e1 = fmaf(D * jv, xx, e1); e2 = fmaf(D * jv, jv, e2); }
                                 }
                             }
@@ -921,9 +927,10 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
 #pragma unroll
             for (int k = 0; k < 3; ++k) { al[k] = fmaf(alpha, xl[k], al[k]); Mal[k] = fmaf(alpha, Mvl[k], Mal[k]); ljar[k] = fmaf(alpha, ljv[k], ljar[k]); }
 #pragma unroll 1
-            for (int c = 0; c < nc; ++c)
-#pragma unroll
-                for (int k = 0; k < NR; ++k) C.jar[k][c] = fmaf(alpha, C.jv[k][c], C.jar[k][c]);
+            for (int c = 0; c < nc; ++c) {
+                const float4 a4 = C.jar[c], v4 = C.jv[c];
+                C.jar[c] = make_float4(fmaf(alpha, v4.x, a4.x), fmaf(alpha, v4.y, a4.y), fmaf(alpha, v4.z, a4.z), fmaf(alpha, v4.w, a4.w));
+            }
             iter++;
             if (flips == 0) conv = true;  // the quadratic model was exact along the whole step: this is the optimum
             // decrease of the cost along the step from the line-search model (-1/2 alpha d1(0) for an exact search on a
@@ -940,16 +947,17 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
             nact_last = 0;
 #pragma unroll 1
             for (int c = 0; c < nc; ++c) {
-                float D = C.D[c], mu = C.mu[c];
-                v3 xc = V3(C.x[c], C.y[c], C.z[c]);
-                int lev = C.lev[c];
+                const float4 g4 = C.geo[c], p4 = C.par[c], j4 = C.jar[c];
+                float D = g4.w, mu = p4.x;
+                v3 xc = V3(g4.x, g4.y, g4.z);
+                int lev = __float_as_int(p4.w);
                 v3 fc;
                 if (CONE) {
-                    EllZ z = ell_eval(C.jar[0][c], C.jar[1][c], C.jar[2][c], mu, mus, D, D * impr);
+                    EllZ z = ell_eval(j4.x, j4.y, j4.z, mu, mus, D, D * impr);
                     nact_last += z.zone ? 3 : 0;
                     fc = fma3(z.f0, up, fma3(z.f1, ty, (-z.f2) * tx));   // rows: n = up, t1 = ty, t2 = -tx
                 } else {
-                    float j0 = C.jar[0][c], j1 = C.jar[1][c], j2 = C.jar[2][c], j3 = C.jar[3][c];
+                    float j0 = j4.x, j1 = j4.y, j2 = j4.z, j3 = j4.w;
                     float f0 = j0 < 0.f ? -D * j0 : 0.f, f1 = j1 < 0.f ? -D * j1 : 0.f;
                     float f2 = j2 < 0.f ? -D * j2 : 0.f, f3 = j3 < 0.f ? -D * j3 : 0.f;
                     nact_last += (j0 < 0.f) + (j1 < 0.f) + (j2 < 0.f) + (j3 < 0.f);
@@ -1015,11 +1023,12 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
             for (int i = 0; i < 21; ++i) Hc[i] = 0.f;
 #pragma unroll 1
             for (int c = 0; c < nc; ++c) {
-                float D = C.D[c], mu = C.mu[c];
+                const float4 g4 = C.geo[c], p4 = C.par[c], j4 = C.jar[c];
+                float D = g4.w, mu = p4.x;
                 // W = 3x3 stiffness of the contact in the basis (e0, e1, e2) = (up, ty, -tx): w00 w11 w22 w01 w02 w12
                 float w00, w11, w22, w01, w02, w12;
                 if (CONE) {
-                    EllZ z = ell_eval(C.jar[0][c], C.jar[1][c], C.jar[2][c], mu, mus, D, D * impr);
+                    EllZ z = ell_eval(j4.x, j4.y, j4.z, mu, mus, D, D * impr);
                     if (z.zone == 0) continue;
                     if (z.zone == 1) { w00 = D; w11 = w22 = D * impr; w01 = w02 = w12 = 0.f; }
                     else {
@@ -1035,16 +1044,16 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                         w12 = stt * stt * (a * z.U1 * z.U2);
                     }
                 } else {
-                    float a0 = C.jar[0][c] < 0.f ? 1.f : 0.f, a1 = C.jar[1][c] < 0.f ? 1.f : 0.f;
-                    float a2 = C.jar[2][c] < 0.f ? 1.f : 0.f, a3 = C.jar[3][c] < 0.f ? 1.f : 0.f;
+                    float a0 = j4.x < 0.f ? 1.f : 0.f, a1 = j4.y < 0.f ? 1.f : 0.f;
+                    float a2 = j4.z < 0.f ? 1.f : 0.f, a3 = j4.w < 0.f ? 1.f : 0.f;
                     float na = a0 + a1 + a2 + a3;
                     if (na == 0.f) continue;
                     // rows w0 = e0 + mu e1, w1 = e0 - mu e1, w2 = e0 + mu e2, w3 = e0 - mu e2
                     w00 = D * na; w11 = D * mu * mu * (a0 + a1); w22 = D * mu * mu * (a2 + a3);
                     w01 = D * mu * (a0 - a1); w02 = D * mu * (a2 - a3); w12 = 0.f;
                 }
-                v3 xc = V3(C.x[c], C.y[c], C.z[c]);
-                int lev = C.lev[c];
+                v3 xc = V3(g4.x, g4.y, g4.z);
+                int lev = __float_as_int(p4.w);
                 // Jacobian columns of the leg joints at the contact point (zero above the contact's link)
                 v3 jc0 = lev >= 1 ? sl[0] + cross(sa[0], xc) : V3(0, 0, 0);
                 v3 jc1 = lev >= 2 ? sl[1] + cross(sa[1], xc) : V3(0, 0, 0);
