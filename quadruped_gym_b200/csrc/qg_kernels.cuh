@@ -157,6 +157,8 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
     // Persistent blocks (one per SM): the model tables are staged once, then the block pulls chunks of
     // blockDim.x / 4 environments from a device counter until the batch is done (dynamic: chunks differ in cost).
     __shared__ int s_chunk;
+    __shared__ unsigned s_ctr[QG_BLOCK / 32][QG_C_COUNT];   // per-warp counters, flushed once when the block is done
+    if ((threadIdx.x & 31) < QG_C_COUNT) s_ctr[threadIdx.x >> 5][threadIdx.x & 31] = 0u;
     const QgDebugOut dbg_in = dbg;
 #pragma unroll 1
     for (;;) {
@@ -177,7 +179,10 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
     const int env = perm ? perm[slot] : slot;
     if (!valid) { dbg.qacc = dbg.qacc_smooth = dbg.qfrc_bias = dbg.M = dbg.sensordata = nullptr; dbg.counts = nullptr; }
     const unsigned qm = 0xFu << (threadIdx.x & 28);
-    unsigned long long cv[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    WarpCounters wc;
+    wc.row = s_ctr[threadIdx.x >> 5];
+    wc.count = valid;
+    wc.lane = threadIdx.x & 31;
     QuadRed qr;
     qr.s = sred;
     qr.lane = threadIdx.x & 31;
@@ -198,8 +203,8 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
         }
 
         StepStats st;
-        st.ncon = st.nefc = st.niter = st.nls = st.nvert = st.overflow = st.nact = 0;
-        st.last_nefc = st.last_iter = 0;
+        st.ncon = st.nefc = st.niter = st.nls = 0;
+        st.last_iter = 0;
         int diverged = 0;
         SensorOut so;
         Contacts C;
@@ -216,7 +221,7 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
                 diverged += (leg == 0);
             }
             physics_step<DEBUG, CONE>(P, sverts, adj4, cadj4, L, leg, qr, wq, max_iter, ls_iter, s == frame_skip - 1, so,
-                                st, C, dbg, env);
+                                st, wc, C, dbg, env);
         }
 
         // ---- reward terms (float64 from the float32 sensordata / ctrl / state, reference formulas)
@@ -309,12 +314,9 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
         }
         if (valid) store_lane(S, N, env, leg, L, episode, first_cc, flags);
 
-        if (valid) {
-        cv[0] = leg == 0 ? frame_skip : 0; cv[1] = st.ncon; cv[2] = st.nefc; cv[3] = st.niter;
-        cv[4] = leg == 0 ? st.nls : 0; cv[5] = st.nvert; cv[6] = diverged; cv[7] = st.overflow;
-        cv[8] = (leg == 0 && term) ? 1 : 0;
-        cv[9] = st.nact;
-        }
+        wc_add(wc, QG_C_STEPS, leg == 0 ? frame_skip : 0);
+        wc_add(wc, QG_C_DIVERGED, diverged);
+        wc_add(wc, QG_C_EPISODES, (leg == 0 && term) ? 1 : 0);
         if (bin_key) {   // key of the next launch's binning: which legs were in contact, and the Newton iterations needed
             int mnc = max(C.n, __shfl_xor_sync(qm, C.n, 1));
             mnc = max(mnc, __shfl_xor_sync(qm, mnc, 2));
@@ -322,18 +324,13 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
         }
     }
 
-    // ---- counters: warp shuffle reduce, one atomic per warp and counter
-    {
-        unsigned long long* out = reinterpret_cast<unsigned long long*>(ctr);
-#pragma unroll
-        for (int i = 0; i < 10; ++i) {
-            unsigned long long x = cv[i];
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-            if ((threadIdx.x & 31) == 0 && x) atomicAdd(out + i, x);
-        }
-    }
     }   // chunk loop
+    // ---- counters: one atomic per warp and counter for the whole launch
+    __syncwarp();
+    if ((threadIdx.x & 31) < QG_C_COUNT) {
+        unsigned v = s_ctr[threadIdx.x >> 5][threadIdx.x & 31];
+        if (v) atomicAdd(reinterpret_cast<unsigned long long*>(ctr) + (threadIdx.x & 31), (unsigned long long)v);
+    }
     // the last block to leave re-arms the chunk counter for the next launch (no host-side state: graph-capture safe)
     if (threadIdx.x == 0) {
         __threadfence();

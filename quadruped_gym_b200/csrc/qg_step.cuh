@@ -39,9 +39,24 @@ struct SensorOut {
     v3 acc, gyro, pos, linvel, xaxis, zaxis, vel;
 };
 
+// Statistics.  The batch counters (qg_get_counters) are kept per WARP in shared memory: at a few warp-converged points
+// of a physics step the lanes' values are summed with one REDUX instruction and lane 0 adds the result to its warp's row;
+// nothing is carried in registers across the step (nine per-lane accumulators cost 2.4 % of the step time through the
+// spills they caused).  Per-environment counts exist only in the DEBUG instantiation (qg_debug_step).
+enum { QG_C_STEPS = 0, QG_C_NCON, QG_C_NEFC, QG_C_NITER, QG_C_NLS, QG_C_NVERT, QG_C_DIVERGED, QG_C_OVERFLOW, QG_C_EPISODES,
+       QG_C_NACT, QG_C_COUNT };
+struct WarpCounters {
+    unsigned* row;   // this warp's QG_C_COUNT counters (shared memory)
+    bool count;      // false for the shadow quads past the end of the batch
+    int lane;
+};
+DI void wc_add(const WarpCounters& w, int i, int v) {   // all 32 lanes must call it together
+    unsigned t = __reduce_add_sync(0xffffffffu, (unsigned)(w.count ? v : 0));
+    if (w.lane == 0) w.row[i] += t;
+}
 struct StepStats {
-    int ncon, nefc, niter, nls, nvert, overflow, nact;   // nact: active rows at the solver's final point
-    int last_nefc, last_iter;   // of the most recent physics step (env totals): the binning key of the next launch
+    int ncon, nefc, niter, nls;   // per lane, DEBUG only
+    int last_iter;                // Newton iterations of the most recent physics step: binning key of the next launch
 };
 
 // per-lane contact table (thread-local memory; only the first `nc` slots are ever touched).  Four float4 per contact
@@ -376,7 +391,7 @@ DI int narrow_phase(const QgModelC& P, const float4* __restrict__ verts, const i
 
 DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const int4* __restrict__ adj4,
                      const int4* __restrict__ cadj4, int leg, const float* fr, v3 up, float zb, Contacts& C,
-                     StepStats& st, const WarpQueue& wq, int lane) {
+                     const WarpCounters& wc, const WarpQueue& wq, int lane) {
     __syncwarp();   // the queue aliases the quad-reduction rows: every quad of the warp is done with them
     const int ng = P.ngeom[leg];
     const int ngmax = max(max(P.ngeom[0], P.ngeom[1]), max(P.ngeom[2], P.ngeom[3]));
@@ -422,10 +437,11 @@ DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const 
                     float imp = impedance(r, G.d0, G.dmax, G.width, G.mid, G.power);
                     C.geo[c] = make_float4(xc.x, xc.y, xc.z, 1.f / fmaxf(1e-15f, (1.f - imp) / imp * G.Rfac));
                     C.par[c] = make_float4(G.mu, G.B, G.K * imp * r, __int_as_float(lev));
-                } else st.overflow++;
+                } else if (wc.count) atomicAdd(wc.row + QG_C_OVERFLOW, 1u);
             }
         }
     };
+    int nvert = 0;                       // vertex evaluations of this lane's narrow phases
     int qn = 0;                          // warp-uniform queue length
     unsigned mine = 0, mine_next = 0;    // this lane's entries: slots of the batch in flight / of the carry-over
     unsigned gs = 0, gs_next = 0;        // their geom ids, 3 bits each, in slot order
@@ -459,7 +475,7 @@ DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const 
             // pass 2: lane i takes queue entry i
             __syncwarp();
             if (lane < nb)
-                wq.rcnt[lane] = narrow_phase(P, verts, adj4, cadj4, wq.qd[lane], wq.qmeta[lane], wq.res + lane * 4, st.nvert);
+                wq.rcnt[lane] = narrow_phase(P, verts, adj4, cadj4, wq.qd[lane], wq.qmeta[lane], wq.res + lane * 4, nvert);
             __syncwarp();
             collect(mine, gs);
             // carry the overflow entries to the front of the queue
@@ -474,13 +490,14 @@ DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const 
         }
     }
     __syncwarp();
+    wc_add(wc, QG_C_NVERT, nvert);
 }
 
 // ---------------------------------------------------------------------------------------------
 template <bool DEBUG, int CONE>
 DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const int4* __restrict__ adj4,
                      const int4* __restrict__ cadj4, LaneState& S, int leg, const QuadRed& qr, const WarpQueue& wq,
-                     int max_iter, int ls_iter, bool want_sensors, SensorOut& so, StepStats& st, Contacts& C,
+                     int max_iter, int ls_iter, bool want_sensors, SensorOut& so, StepStats& st, const WarpCounters& wc, Contacts& C,
                      const QgDebugOut& dbg, int env) {
     const float h = P.timestep;
     constexpr int NR = CONE ? 3 : 4;   // rows per contact
@@ -521,7 +538,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
         }
     }
     C.n = 0;
-    collide_lane(P, verts, adj4, cadj4, leg, fr, up, zb, C, st, wq, qr.lane);
+    collide_lane(P, verts, adj4, cadj4, leg, fr, up, zb, C, wc, wq, qr.lane);
 #if QG_BLOCKSYNC >= 2
     __syncthreads();  // collision time varies per warp: re-align before the straight-line dynamics code
 #endif
@@ -705,8 +722,9 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
     qr_sync(qr);
     const int nefc = (int)qr_get(qr, 0);
     qr_sync(qr);
-    st.ncon += nc;
-    st.nefc += NR * nc + nlim;
+    wc_add(wc, QG_C_NCON, nc);
+    wc_add(wc, QG_C_NEFC, NR * nc + nlim);
+    if (DEBUG) { st.ncon += nc; st.nefc += NR * nc + nlim; }
 
     // ---- phase machine around ONE arrow solve: 0 = unconstrained acceleration (H = M, rhs = qfrc_smooth),
     //      1 = Newton direction (H = M + J^T D J, rhs = -grad), 2 = implicit integration
@@ -722,7 +740,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
     for (int i = 0; i < 21; ++i) Hc[i] = 0.f;
 #pragma unroll
     for (int i = 0; i < 3; ++i) { rl[i] = fsl[i]; fcl[i] = 0.f; }
-    int phase = 0, iter = 0, nact_last = 0;
+    int phase = 0, iter = 0, nact_last = 0, nls = 0;
     float impr_est = 0.f;
     bool done = false;
 #pragma unroll 1
@@ -872,7 +890,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
             flips = (int)qr_get(qr, 2);
             const float z1s = qr_get(qr, 3), e1s = qr_get(qr, 4), e2s = qr_get(qr, 5);
             qr_sync(qr);
-            st.nls++;
+            nls++;
             float alpha = 1.f;
             const float d10 = z1s + q1;                                // derivative at 0 (< 0: descent direction)
             if (flips != 0) {
@@ -917,7 +935,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                         d1 = qr_get(qr, 0) + q1 + 2.f * alpha * q2;
                         d2 = qr_get(qr, 1) + 2.f * q2;
                         qr_sync(qr);
-                        st.nls++;
+                        nls++;
                     }
                 }
             }
@@ -1102,10 +1120,11 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
             phase = 1;
         }
     }
-    st.niter += (leg == 0) ? iter : 0;
-    st.last_nefc = nefc;
+    wc_add(wc, QG_C_NITER, leg == 0 ? iter : 0);
+    wc_add(wc, QG_C_NLS, leg == 0 ? nls : 0);
+    wc_add(wc, QG_C_NACT, nact_last);
+    if (DEBUG) { st.niter += (leg == 0) ? iter : 0; st.nls += nls; }
     st.last_iter = iter;
-    st.nact += nact_last;
 
     // ---- sensors of this forward pass (pre-integration state, solver qacc)
     if (want_sensors) {
