@@ -654,20 +654,19 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
     }
 
     // ---- passive + actuation -> qfrc_smooth (B form)
-    float fsb[6], fsl[3], act_dot[3], dimp[3];  // dimp: implicit-integrator diagonal (damping + servo kv)
+    float fsb[6], fsl[3];
+    int unclamped = 0;   // bit k: servo k is not force-clamped (its kv term enters the implicit integrator's diagonal)
     fsb[0] = -P.base_damp[0] * vB.x - fsum.x; fsb[1] = -P.base_damp[1] * vB.y - fsum.y; fsb[2] = -P.base_damp[2] * vB.z - fsum.z;
     fsb[3] = -P.base_damp[3] * S.om.x - nsum.x; fsb[4] = -P.base_damp[4] * S.om.y - nsum.y; fsb[5] = -P.base_damp[5] * S.om.z - nsum.z;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const QgJointC& J = P.joint[leg][k];
         float tau = 0.f;
-        act_dot[k] = 0.f;
-        dimp[k] = J.damping;
         if (J.has_act) {
             float c = S.ctrl[k];
             if (J.ctrl_limited) c = fminf(fmaxf(c, J.ctrl_lo), J.ctrl_hi);
             float ain = c;
-            if (J.has_dyn) { act_dot[k] = (c - S.act[k]) * J.inv_tau; ain = S.act[k]; }
+            if (J.has_dyn) ain = S.act[k];
             float f = fmaf(J.kp, ain, J.b0) + J.b1 * (J.gear * S.q[k]) + J.b2 * (J.gear * S.qd[k]);
             bool clamped = false;
             if (J.frc_limited) {
@@ -675,7 +674,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                 else if (f >= J.frc_hi) { f = J.frc_hi; clamped = true; }
             }
             tau = J.gear * f;
-            if (!clamped && P.integrator == 1) dimp[k] -= J.gear * J.gear * J.b2;
+            if (!clamped && P.integrator == 1) unclamped |= 1 << k;
         }
         fsl[k] = -J.damping * S.qd[k] - bias_l[k] + tau;
     }
@@ -730,16 +729,15 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
     //      1 = Newton direction (H = M + J^T D J, rhs = -grad), 2 = implicit integration
     //      (H = M + h*diag, rhs = qfrc_smooth + qfrc_constraint)
     float ab[6], al[3], a0b[6], a0l[3], Mab[6], Mal[3];
-    float fcb[6], fcl[3];
     float Hll[6], Hbl[18], Hc[21], rb[6], rl[3], xb[6], xl[3];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { Hll[i] = Mll[i]; rb[i] = fsb[i]; fcb[i] = 0.f; }
+    for (int i = 0; i < 6; ++i) { Hll[i] = Mll[i]; rb[i] = fsb[i]; }
 #pragma unroll
     for (int i = 0; i < 18; ++i) Hbl[i] = Mbl[i];
 #pragma unroll
     for (int i = 0; i < 21; ++i) Hc[i] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { rl[i] = fsl[i]; fcl[i] = 0.f; }
+    for (int i = 0; i < 3; ++i) rl[i] = fsl[i];
     int phase = 0, iter = 0, nact_last = 0, nls = 0;
     float impr_est = 0.f;
     bool done = false;
@@ -1001,9 +999,11 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
             qr_put(qr, 4, Nb.x); qr_put(qr, 5, Nb.y); qr_put(qr, 6, Nb.z);
             float g2 = 0.f, g2b = 0.f;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { fcl[k] = tau[k]; gl[k] = Mal[k] - fsl[k] - tau[k]; g2 += gl[k] * gl[k]; }
+            for (int k = 0; k < 3; ++k) { gl[k] = Mal[k] - fsl[k] - tau[k]; g2 += gl[k] * gl[k]; }
             qr_put(qr, 7, g2);
             qr_sync(qr);
+#pragma unroll
+            float fcb[6];
 #pragma unroll
             for (int r = 0; r < 6; ++r) fcb[r] = qr_get(qr, 1 + r);
             g2 = qr_get(qr, 7);
@@ -1021,15 +1021,24 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
             // ---- next solve: implicit integration  (M + h*diag) qacc+ = qfrc_smooth + qfrc_constraint
 #pragma unroll
             for (int i = 0; i < 6; ++i) Hll[i] = Mll[i];
-            Hll[0] += h * dimp[0]; Hll[3] += h * dimp[1]; Hll[5] += h * dimp[2];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {   // implicit-integrator diagonal: damping + servo kv (unless force-clamped)
+                const QgJointC& J = P.joint[leg][k];
+                float dk = J.damping - (((unclamped >> k) & 1) ? J.gear * J.gear * J.b2 : 0.f);
+                Hll[k == 0 ? 0 : (k == 1 ? 3 : 5)] += h * dk;
+            }
 #pragma unroll
             for (int i = 0; i < 18; ++i) Hbl[i] = Mbl[i];
 #pragma unroll
             for (int i = 0; i < 21; ++i) Hc[i] = 0.f;
 #pragma unroll
-            for (int r = 0; r < 6; ++r) { Hc[IX6(r, r)] = (leg == 0) ? h * P.base_damp[r] : 0.f; rb[r] = fsb[r] + fcb[r]; }
+            for (int r = 0; r < 6; ++r) {
+                Hc[IX6(r, r)] = (leg == 0) ? h * P.base_damp[r] : 0.f;
+                // qfrc_smooth + qfrc_constraint = M a - gradient at the solver's final point (no copy of the force kept)
+                rb[r] = (nefc > 0) ? Mab[r] - gb[r] : fsb[r];
+            }
 #pragma unroll
-            for (int k = 0; k < 3; ++k) rl[k] = fsl[k] + fcl[k];
+            for (int k = 0; k < 3; ++k) rl[k] = (nefc > 0) ? Mal[k] - gl[k] : fsl[k];
             phase = 2;
         } else {
             // ---- next solve: Newton direction.  H = M + J^T D J over the active rows
@@ -1184,7 +1193,14 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         S.wj[k] = al[k];
-        S.act[k] = fmaf(act_dot[k], P.joint[leg][k].act_fac, S.act[k]);
+        {   // activation dynamics: act_dot = (clamp(ctrl) - act) / tau, exact first-order filter over h
+            const QgJointC& J = P.joint[leg][k];
+            if (J.has_act && J.has_dyn) {
+                float c = S.ctrl[k];
+                if (J.ctrl_limited) c = fminf(fmaxf(c, J.ctrl_lo), J.ctrl_hi);
+                S.act[k] = fmaf((c - S.act[k]) * J.inv_tau, J.act_fac, S.act[k]);
+            }
+        }
         S.qd[k] = fmaf(h, xl[k], S.qd[k]);
         S.q[k] = fmaf(h, S.qd[k], S.q[k]);
     }
