@@ -200,6 +200,7 @@ DI void twist(const float* xb, const float* xl, const v3* sl, const v3* sa, v3* 
         W[j + 1] = fma3(xl[j], sa[j], W[j]);
     }
 }
+DI float sel3(const float* a, int k) { return k == 0 ? a[0] : (k == 1 ? a[1] : a[2]); }
 DI v3 sel4(const v3* A, int lev) { return lev == 0 ? A[0] : (lev == 1 ? A[1] : (lev == 2 ? A[2] : A[3])); }
 
 // rows of the 4-sided friction pyramid for a point velocity u: n + mu t1, n - mu t1, n + mu t2, n - mu t2
@@ -680,13 +681,15 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
     }
 
     // ---- constraint rows: joint limits (own dofs) and pyramidal contacts (table C); jar starts as -aref
-    float lsgn[3], lD[3], ljar[3], ljv[3];
+    // Active limits are rare (a joint past its range): they live in a thread-local table indexed by a run-time slot, so
+    // that they cost a loop that is skipped instead of 12 registers held across the whole solve.
+    // Record: (sign * (dof + 1), D, J a - aref, J v).
+    float4 lim[3];
     int nlim = 0;
     v3 U[4], W[4];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const QgJointC& J = P.joint[leg][k];
-        lsgn[k] = 0.f; lD[k] = 0.f; ljar[k] = 0.f; ljv[k] = 0.f;
         if (J.limited) {
             float dlo = S.q[k] - J.lo, dhi = J.hi - S.q[k];
             float dist = 0.f, sg = 0.f;
@@ -694,9 +697,8 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
             else if (dhi < 0.f) { dist = dhi; sg = -1.f; }
             if (sg != 0.f) {
                 float imp = impedance(dist, P.lim_d0, P.lim_dmax, P.lim_width, P.lim_mid, P.lim_power);
-                lsgn[k] = sg;
-                lD[k] = 1.f / fmaxf(1e-15f, (1.f - imp) / imp * J.invw_dof);
-                ljar[k] = P.lim_B * (sg * S.qd[k]) + P.lim_K * imp * dist;  // = -aref
+                lim[nlim] = make_float4(sg * (float)(k + 1), 1.f / fmaxf(1e-15f, (1.f - imp) / imp * J.invw_dof),
+                                        P.lim_B * (sg * S.qd[k]) + P.lim_K * imp * dist /* = -aref */, 0.f);
                 nlim++;
             }
         }
@@ -802,14 +804,15 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                         cs += ell_eval(rs[0], rs[1], rs[2], p4.x, mus, D, D * impr).cost;
                     }
                 }
-                float ljs[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    float jw = fmaf(lsgn[k], S.wj[k], ljar[k]), js = fmaf(lsgn[k], a0l[k], ljar[k]);
-                    ljs[k] = js;
-                    ljar[k] = jw;
-                    cw += (lsgn[k] != 0.f && jw < 0.f) ? 0.5f * lD[k] * jw * jw : 0.f;
-                    cs += (lsgn[k] != 0.f && js < 0.f) ? 0.5f * lD[k] * js * js : 0.f;
+#pragma unroll 1
+                for (int s = 0; s < nlim; ++s) {
+                    float4 r = lim[s];
+                    const int k = (int)fabsf(r.x) - 1;
+                    const float sg = r.x < 0.f ? -1.f : 1.f;
+                    float jw = fmaf(sg, sel3(S.wj, k), r.z), js = fmaf(sg, sel3(a0l, k), r.z);
+                    cw += (jw < 0.f) ? 0.5f * r.y * jw * jw : 0.f;
+                    cs += (js < 0.f) ? 0.5f * r.y * js * js : 0.f;
+                    lim[s] = make_float4(r.x, r.y, jw, js);   // .w parks the value at qacc_smooth
                 }
                 float Mwb[6], Mwl[3];
                 arrow_matvec(Mll, Mbl, Mbb, wb, S.wj, qr, Mwb, Mwl);
@@ -830,8 +833,8 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                 } else {
 #pragma unroll 1
                     for (int c = 0; c < nc; ++c) C.jar[c] = C.jv[c];
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) ljar[k] = ljs[k];
+#pragma unroll 1
+                    for (int s = 0; s < nlim; ++s) { float4 r = lim[s]; r.z = r.w; lim[s] = r; }
                 }
             }
         } else {
@@ -871,15 +874,16 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                     }
                 }
             }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                ljv[k] = lsgn[k] * xl[k];
-                if (lsgn[k] != 0.f) {
-                    float j0 = ljar[k], j1 = j0 + ljv[k];
-                    if (j0 < 0.f) { z1 = fmaf(lD[k] * ljv[k], j0, z1); z2 = fmaf(lD[k] * ljv[k], ljv[k], z2); }
-                    if (j1 < 0.f) { e1 = fmaf(lD[k] * ljv[k], j1, e1); e2 = fmaf(lD[k] * ljv[k], ljv[k], e2); }
-                    flips += ((j0 < 0.f) != (j1 < 0.f)) ? 1 : 0;
-                }
+#pragma unroll 1
+            for (int s = 0; s < nlim; ++s) {
+                float4 r = lim[s];
+                const int k = (int)fabsf(r.x) - 1;
+                const float jv = (r.x < 0.f ? -1.f : 1.f) * sel3(xl, k), j0 = r.z, j1 = j0 + jv;
+                if (j0 < 0.f) { z1 = fmaf(r.y * jv, j0, z1); z2 = fmaf(r.y * jv, jv, z2); }
+                if (j1 < 0.f) { e1 = fmaf(r.y * jv, j1, e1); e2 = fmaf(r.y * jv, jv, e2); }
+                flips += ((j0 < 0.f) != (j1 < 0.f)) ? 1 : 0;
+                r.w = jv;
+                lim[s] = r;
             }
             qr_put(qr, 0, q1l); qr_put(qr, 1, q2l); qr_put(qr, 2, (float)flips);
             qr_put(qr, 3, z1); qr_put(qr, 4, e1); qr_put(qr, 5, e2);
@@ -923,10 +927,11 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                                 }
                             }
                         }
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            float xx = fmaf(alpha, ljv[k], ljar[k]);
-                            if (lsgn[k] != 0.f && xx < 0.f) { e1 = fmaf(lD[k] * ljv[k], xx, e1); e2 = fmaf(lD[k] * ljv[k], ljv[k], e2); }
+#pragma unroll 1
+                        for (int s = 0; s < nlim; ++s) {
+                            const float4 r = lim[s];
+                            float xx = fmaf(alpha, r.w, r.z);
+                            if (xx < 0.f) { e1 = fmaf(r.y * r.w, xx, e1); e2 = fmaf(r.y * r.w, r.w, e2); }
                         }
                         qr_put(qr, 0, e1); qr_put(qr, 1, e2);
                         qr_sync(qr);
@@ -941,7 +946,9 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
 #pragma unroll
             for (int r = 0; r < 6; ++r) { ab[r] = fmaf(alpha, xb[r], ab[r]); Mab[r] = fmaf(alpha, Mvb[r], Mab[r]); }
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { al[k] = fmaf(alpha, xl[k], al[k]); Mal[k] = fmaf(alpha, Mvl[k], Mal[k]); ljar[k] = fmaf(alpha, ljv[k], ljar[k]); }
+            for (int k = 0; k < 3; ++k) { al[k] = fmaf(alpha, xl[k], al[k]); Mal[k] = fmaf(alpha, Mvl[k], Mal[k]); }
+#pragma unroll 1
+            for (int s = 0; s < nlim; ++s) { float4 r = lim[s]; r.z = fmaf(alpha, r.w, r.z); lim[s] = r; }
 #pragma unroll 1
             for (int c = 0; c < nc; ++c) {
                 const float4 a4 = C.jar[c], v4 = C.jv[c];
@@ -987,12 +994,14 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                 tau[1] += lev >= 2 ? dot(sl[1], fc) + dot(sa[1], nn) : 0.f;
                 tau[2] += lev >= 3 ? dot(sl[2], fc) + dot(sa[2], nn) : 0.f;
             }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (lsgn[k] != 0.f && ljar[k] < 0.f) {
-                    float f = -lD[k] * ljar[k];
+#pragma unroll 1
+            for (int s = 0; s < nlim; ++s) {
+                const float4 r = lim[s];
+                if (r.z < 0.f) {
+                    const int k = (int)fabsf(r.x) - 1;
+                    const float t = (r.x < 0.f ? 1.f : -1.f) * r.y * r.z;   // sign * f,  f = -D * jar
                     nact_last++;
-                    tau[k] += lsgn[k] * f;
+                    tau[0] += k == 0 ? t : 0.f; tau[1] += k == 1 ? t : 0.f; tau[2] += k == 2 ? t : 0.f;
                 }
             }
             qr_put(qr, 1, Fb.x); qr_put(qr, 2, Fb.y); qr_put(qr, 3, Fb.z);
@@ -1119,9 +1128,14 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                 Hc[IX6(3, 3)] += r3.x; Hc[IX6(4, 3)] += r4.x; Hc[IX6(4, 4)] += r4.y;
                 Hc[IX6(5, 3)] += r5.x; Hc[IX6(5, 4)] += r5.y; Hc[IX6(5, 5)] += r5.z;
             }
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-                if (lsgn[k] != 0.f && ljar[k] < 0.f) Hll[k == 0 ? 0 : (k == 1 ? 3 : 5)] += lD[k];
+#pragma unroll 1
+            for (int s = 0; s < nlim; ++s) {
+                const float4 r = lim[s];
+                if (r.z < 0.f) {
+                    const int k = (int)fabsf(r.x) - 1;
+                    Hll[0] += k == 0 ? r.y : 0.f; Hll[3] += k == 1 ? r.y : 0.f; Hll[5] += k == 2 ? r.y : 0.f;
+                }
+            }
 #pragma unroll
             for (int r = 0; r < 6; ++r) rb[r] = -gb[r];
 #pragma unroll
