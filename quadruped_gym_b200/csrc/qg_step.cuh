@@ -1011,7 +1011,6 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
             for (int k = 0; k < 3; ++k) { gl[k] = Mal[k] - fsl[k] - tau[k]; g2 += gl[k] * gl[k]; }
             qr_put(qr, 7, g2);
             qr_sync(qr);
-#pragma unroll
             float fcb[6];
 #pragma unroll
             for (int r = 0; r < 6; ++r) fcb[r] = qr_get(qr, 1 + r);
