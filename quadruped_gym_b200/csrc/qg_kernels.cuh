@@ -317,7 +317,7 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
         wc_add(wc, QG_C_STEPS, leg == 0 ? frame_skip : 0);
         wc_add(wc, QG_C_DIVERGED, diverged);
         wc_add(wc, QG_C_EPISODES, (leg == 0 && term) ? 1 : 0);
-        if (bin_key) {   // key of the next launch's binning: which legs were in contact, and the Newton iterations needed
+        if (bin_key) {   // key of the next launch's binning: largest per-leg contact count x Newton iterations of the last physics step
             int mnc = max(C.n, __shfl_xor_sync(qm, C.n, 1));
             mnc = max(mnc, __shfl_xor_sync(qm, mnc, 2));
             if (leg == 0 && valid) bin_key[env] = (unsigned char)(min(mnc, 7) * 8 + min(st.last_iter, 7));
