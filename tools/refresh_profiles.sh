@@ -5,7 +5,7 @@
 set -euo pipefail
 cd "$(dirname "${BASH_SOURCE[0]}")/.."
 for f in r1_bench.json r1_bench_c2.json r1_bench_c4.json r1_bench_c5.json r1_bench_ref.json r1_scale_2.json r1_scale_4.json \
-         r1_scale_8.json r1_pytest_gpu.log r1_smoke.log r1_validation.txt r1_same_actions.log r1_env_throughput.txt r1_launches.csv; do
+         r1_scale_8.json r1_gpu_check.txt r1_pytest_gpu.log r1_smoke.log r1_validation.txt r1_same_actions.log r1_env_throughput.txt r1_launches.csv; do
   [ -f gpurun_out/$f ] && cp gpurun_out/$f profiles/$f
 done
 cp profiles/r1_bench.json profiles/r1_scale_1.json
