@@ -190,6 +190,20 @@ DI void arrow_matvec(const float* Mll, const float* Mbl, const float* Mbb, const
     qr_sync(qr);
 }
 
+// lane-local half of the same product: yl complete, yb_part = this lane's coupling contribution to the base rows
+DI void arrow_matvec_local(const float* Mll, const float* Mbl, const float* xb, const float* xl, float* yb_part, float* yl) {
+    yl[0] = fmaf(Mll[0], xl[0], fmaf(Mll[1], xl[1], Mll[2] * xl[2]));
+    yl[1] = fmaf(Mll[1], xl[0], fmaf(Mll[3], xl[1], Mll[4] * xl[2]));
+    yl[2] = fmaf(Mll[2], xl[0], fmaf(Mll[4], xl[1], Mll[5] * xl[2]));
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        yl[0] = fmaf(Mbl[r * 3], xb[r], yl[0]);
+        yl[1] = fmaf(Mbl[r * 3 + 1], xb[r], yl[1]);
+        yl[2] = fmaf(Mbl[r * 3 + 2], xb[r], yl[2]);
+        yb_part[r] = fmaf(Mbl[r * 3], xl[0], fmaf(Mbl[r * 3 + 1], xl[1], Mbl[r * 3 + 2] * xl[2]));
+    }
+}
+
 // spatial velocity prefixes of a generalised vector: U[k] + W[k] x p = velocity of a point p on link k
 DI void twist(const float* xb, const float* xl, const v3* sl, const v3* sa, v3* U, v3* W) {
     U[0] = V3(xb[0], xb[1], xb[2]);
@@ -839,13 +853,13 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
             }
         } else {
             // ---- (xb, xl) is the Newton direction: exact line search on the convex piecewise quadratic
-            float Mvb[6], Mvl[3];
-            arrow_matvec(Mll, Mbl, Mbb, xb, xl, qr, Mvb, Mvl);
+            // M v: the lane-local part now, the base rows after the line search's own reduction (their six partial sums
+            // ride in the same shared-memory round trip instead of a separate one)
+            float Mvb[6], Mvl[3], Mvp[6];
+            arrow_matvec_local(Mll, Mbl, xb, xl, Mvp, Mvl);
             float q1l = 0.f, q2l = 0.f, q1b = 0.f, q2b = 0.f;
 #pragma unroll
             for (int k = 0; k < 3; ++k) { q1l += xl[k] * (Mal[k] - fsl[k]); q2l += 0.5f * xl[k] * Mvl[k]; }
-#pragma unroll
-            for (int r = 0; r < 6; ++r) { q1b += xb[r] * (Mab[r] - fsb[r]); q2b += 0.5f * xb[r] * Mvb[r]; }
             twist(xb, xl, sl, sa, U, W);
             // first trial alpha = 1 (the exact minimiser when no row changes state along the step)
             float e1 = 0.f, e2 = 0.f, z1 = 0.f, z2 = 0.f;
@@ -887,7 +901,18 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
             }
             qr_put(qr, 0, q1l); qr_put(qr, 1, q2l); qr_put(qr, 2, (float)flips);
             qr_put(qr, 3, z1); qr_put(qr, 4, e1); qr_put(qr, 5, e2);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) qr_put(qr, 6 + r, Mvp[r]);
             qr_sync(qr);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                float t = 0.f;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) t = fmaf(Mbb[r >= k ? IX6(r, k) : IX6(k, r)], xb[k], t);
+                Mvb[r] = t + qr_get(qr, 6 + r);
+                q1b += xb[r] * (Mab[r] - fsb[r]);
+                q2b += 0.5f * xb[r] * Mvb[r];
+            }
             const float q1 = qr_get(qr, 0) + q1b, q2 = qr_get(qr, 1) + q2b;
             flips = (int)qr_get(qr, 2);
             const float z1s = qr_get(qr, 3), e1s = qr_get(qr, 4), e2s = qr_get(qr, 5);
