@@ -104,3 +104,12 @@ def test_missing_extension_fails_loudly(tmp_path):
             "try:\n    _lib.lib()\nexcept _lib.QuadGymLibraryError as e:\n    print('RAISED', 'no CPU fallback' in str(e))\n") % (ROOT, str(tmp_path / "nope.so"))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert out.stdout.strip() == "RAISED True", out.stdout + out.stderr
+
+
+def test_top_level_exports_resolve_lazily():
+    """The package face a reference user switches to: every advertised name resolves (no GPU, no .so call needed)."""
+    import quadruped_gym_b200 as q
+    for name in q.__all__:
+        assert getattr(q, name) is not None
+    with pytest.raises(AttributeError):
+        getattr(q, "NoSuchEnv")
