@@ -165,32 +165,8 @@ DI void arrow_solve(const float* All, const float* Abl, const float* Alocal, con
 #undef LEG_SOLVE
 }
 
-// y = M x on the arrow pattern
-DI void arrow_matvec(const float* Mll, const float* Mbl, const float* Mbb, const float* xb, const float* xl,
-                     const QuadRed& qr, float* yb, float* yl) {
-    yl[0] = fmaf(Mll[0], xl[0], fmaf(Mll[1], xl[1], Mll[2] * xl[2]));
-    yl[1] = fmaf(Mll[1], xl[0], fmaf(Mll[3], xl[1], Mll[4] * xl[2]));
-    yl[2] = fmaf(Mll[2], xl[0], fmaf(Mll[4], xl[1], Mll[5] * xl[2]));
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-        yl[0] = fmaf(Mbl[r * 3], xb[r], yl[0]);
-        yl[1] = fmaf(Mbl[r * 3 + 1], xb[r], yl[1]);
-        yl[2] = fmaf(Mbl[r * 3 + 2], xb[r], yl[2]);
-    }
-#pragma unroll
-    for (int r = 0; r < 6; ++r) qr_put(qr, r, fmaf(Mbl[r * 3], xl[0], fmaf(Mbl[r * 3 + 1], xl[1], Mbl[r * 3 + 2] * xl[2])));
-    qr_sync(qr);
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-        float t = 0.f;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) t = fmaf(Mbb[r >= k ? IX6(r, k) : IX6(k, r)], xb[k], t);
-        yb[r] = t + qr_get(qr, r);
-    }
-    qr_sync(qr);
-}
-
-// lane-local half of the same product: yl complete, yb_part = this lane's coupling contribution to the base rows
+// y = M x on the arrow pattern, the lane-local half: yl complete, yb_part = this lane's coupling contribution to the base
+// rows (the caller adds Mbb xb and the quad sum of yb_part, inside a reduction it needs anyway)
 DI void arrow_matvec_local(const float* Mll, const float* Mbl, const float* xb, const float* xl, float* yb_part, float* yl) {
     yl[0] = fmaf(Mll[0], xl[0], fmaf(Mll[1], xl[1], Mll[2] * xl[2]));
     yl[1] = fmaf(Mll[1], xl[0], fmaf(Mll[3], xl[1], Mll[4] * xl[2]));
@@ -594,6 +570,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
 
     // ---- backward pass: composite inertias -> M blocks, RNE forces -> bias
     float Mll[6], Mbl[18], Mbb[21];
+    int nefc = 0;   // constraint rows of the environment (quad sum)
     float bias_l[3];
     v3 fsum = V3(0, 0, 0), nsum = V3(0, 0, 0);
     float cm = 0.f;
@@ -643,6 +620,15 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
         qr_put(qr, 6, cm); qr_put(qr, 7, chv.x); qr_put(qr, 8, chv.y); qr_put(qr, 9, chv.z);
         qr_put(qr, 10, cI.xx); qr_put(qr, 11, cI.yy); qr_put(qr, 12, cI.zz);
         qr_put(qr, 13, cI.xy); qr_put(qr, 14, cI.xz); qr_put(qr, 15, cI.yz);
+        {   // the environment's constraint-row count rides along (same tests as the row setup below)
+            int nl = 0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const QgJointC& J = P.joint[leg][k];
+                nl += (J.limited && (S.q[k] - J.lo < 0.f || J.hi - S.q[k] < 0.f)) ? 1 : 0;
+            }
+            qr_put(qr, 16, (float)(NR * C.n + nl));
+        }
         qr_sync(qr);
         fsum = V3(qr_get(qr, 0), qr_get(qr, 1), qr_get(qr, 2)) + F0;
         nsum = V3(qr_get(qr, 3), qr_get(qr, 4), qr_get(qr, 5)) + N0;
@@ -656,6 +642,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
         It.xy = qr_get(qr, 13) + I0.xy - m0 * c0.x * c0.y;
         It.xz = qr_get(qr, 14) + I0.xz - m0 * c0.x * c0.z;
         It.yz = qr_get(qr, 15) + I0.yz - m0 * c0.y * c0.z;
+        nefc = (int)qr_get(qr, 16);
         qr_sync(qr);
 #pragma unroll
         for (int i = 0; i < 21; ++i) Mbb[i] = 0.f;
@@ -733,10 +720,6 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
         for (int k = 0; k < NR; ++k) jr[k] = fmaf(p4.y, rv[k], (CONE && k > 0) ? 0.f : p4.z);  // = -aref_k
         C.jar[c] = st4(jr);
     }
-    qr_put(qr, 0, (float)(NR * nc + nlim));
-    qr_sync(qr);
-    const int nefc = (int)qr_get(qr, 0);
-    qr_sync(qr);
     wc_add(wc, QG_C_NCON, nc);
     wc_add(wc, QG_C_NEFC, NR * nc + nlim);
     if (DEBUG) { st.ncon += nc; st.nefc += NR * nc + nlim; }
@@ -828,15 +811,24 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                     cs += (js < 0.f) ? 0.5f * r.y * js * js : 0.f;
                     lim[s] = make_float4(r.x, r.y, jw, js);   // .w parks the value at qacc_smooth
                 }
-                float Mwb[6], Mwl[3];
-                arrow_matvec(Mll, Mbl, Mbb, wb, S.wj, qr, Mwb, Mwl);
+                // M w: lane-local part now, base rows from the same reduction that sums the two costs
+                float Mwb[6], Mwl[3], Mwp[6];
+                arrow_matvec_local(Mll, Mbl, wb, S.wj, Mwp, Mwl);
                 float gl = 0.f, gb = 0.f;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) gl += 0.5f * (Mwl[k] - fsl[k]) * (S.wj[k] - a0l[k]);
-#pragma unroll
-                for (int r = 0; r < 6; ++r) gb += 0.5f * (Mwb[r] - fsb[r]) * (wb[r] - a0b[r]);
                 qr_put(qr, 0, cw + gl); qr_put(qr, 1, cs);
+#pragma unroll
+                for (int r = 0; r < 6; ++r) qr_put(qr, 2 + r, Mwp[r]);
                 qr_sync(qr);
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) t = fmaf(Mbb[r >= k ? IX6(r, k) : IX6(k, r)], wb[k], t);
+                    Mwb[r] = t + qr_get(qr, 2 + r);
+                    gb += 0.5f * (Mwb[r] - fsb[r]) * (wb[r] - a0b[r]);
+                }
                 float cost_w = qr_get(qr, 0) + gb, cost_s = qr_get(qr, 1);
                 qr_sync(qr);
                 if (cost_w < cost_s) {
