@@ -4,7 +4,7 @@
 # tools/README.md have written gpurun_out/{prof_final.ncu-rep, r1_launches.csv, r1_*.json, r1_*.log, r1_*.txt}.
 set -euo pipefail
 cd "$(dirname "${BASH_SOURCE[0]}")/.."
-for f in r1_bench.json r1_bench_c2.json r1_bench_c4.json r1_bench_c5.json r1_bench_ref.json r1_scale_2.json r1_scale_4.json \
+for f in r1_bench.json r1_bench_c2.json r1_bench_c4.json r1_bench_c5.json r1_bench_c5_8gpu.json r1_bench_ref.json r1_scale_2.json r1_scale_4.json \
          r1_scale_8.json r1_gpu_check.txt r1_pytest_gpu.log r1_smoke.log r1_validation.txt r1_same_actions.log r1_env_throughput.txt r1_launches.csv; do
   [ -f gpurun_out/$f ] && cp gpurun_out/$f profiles/$f
 done
