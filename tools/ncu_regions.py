@@ -2,7 +2,7 @@
 chains of nvdisasm --print-line-info-inline.  Usage: ncu_regions.py rep.ncu-rep"""
 import collections, csv, io, os, re, subprocess, sys, tempfile
 rep = sys.argv[1]
-ksub = "qg_step_kernelILb0ELi0"
+ksub = os.environ.get("NCU_KSUB", "qg_step_kernelILb0ELi0")
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.environ.get("QG_LIB", os.path.join(root, "quadruped_gym_b200", "libquadgym.so"))
 tmp = tempfile.mkdtemp()
