@@ -512,7 +512,7 @@ extern "C" int qg_batch_create(const qg_model* m, int n_envs, int device, qg_bat
     CUDA_OK(cudaMemset(b->d_chunk, 0, 2 * sizeof(int)));
     b->perm_valid = false;
     // environment binning (slot -> env permutation refreshed every step from the last physics step's per-leg contact count
-    // and Newton iterations): measured -2 % step time at 65,536 envs, for 2 extra tiny launches per step.  On by default
+    // and line-search evaluations): measured -2 % step time at 65,536 envs, for 2 extra tiny launches per step.  On by default
     // only for batches large enough to pay for those; QG_BINNING=0/1 overrides.  Results per environment do not depend
     // on the slot (test_env_binning_does_not_change_results).
     b->binning = n_envs >= 32768;

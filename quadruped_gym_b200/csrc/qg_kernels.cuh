@@ -204,7 +204,7 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
 
         StepStats st;
         st.ncon = st.nefc = st.niter = st.nls = 0;
-        st.last_iter = 0;
+        st.last_ls = 0;
         int diverged = 0;
         SensorOut so;
         Contacts C;
@@ -317,10 +317,10 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
         wc_add(wc, QG_C_STEPS, leg == 0 ? frame_skip : 0);
         wc_add(wc, QG_C_DIVERGED, diverged);
         wc_add(wc, QG_C_EPISODES, (leg == 0 && term) ? 1 : 0);
-        if (bin_key) {   // key of the next launch's binning: largest per-leg contact count x Newton iterations of the last physics step
+        if (bin_key) {   // key of the next launch's binning: largest per-leg contact count x line-search evaluations of the last physics step
             int mnc = max(C.n, __shfl_xor_sync(qm, C.n, 1));
             mnc = max(mnc, __shfl_xor_sync(qm, mnc, 2));
-            if (leg == 0 && valid) bin_key[env] = (unsigned char)(min(mnc, 7) * 8 + min(st.last_iter, 7));
+            if (leg == 0 && valid) bin_key[env] = (unsigned char)(min(mnc, 7) * 8 + min(st.last_ls, 7));
         }
     }
 
@@ -439,8 +439,9 @@ __global__ void qg_ffma_kernel(float* out, int iters, float a, float b) {
 
 
 // ---------------------------------------------------------------------------------------------
-// Counting sort of the environments by the key the step kernel left (64 bins: largest per-leg contact count x Newton
-// iterations of the last physics step -- the two trip counts a warp pays the maximum of).  Two tiny launches per env.step(); the order inside a bin is irrelevant.
+// Counting sort of the environments by the key the step kernel left (64 bins: largest per-leg contact count x line-search
+// evaluations of the last physics step -- the trip counts a warp pays the maximum of; evaluations separate the
+// environments slightly better than Newton iterations: 1.402 -> 1.394 ms).  Two tiny launches per env.step(); the order inside a bin is irrelevant.
 #define QG_NBINS 64
 __global__ void qg_bin_hist_kernel(const unsigned char* __restrict__ key, int N, int* __restrict__ count) {
     __shared__ int sc[QG_NBINS];

@@ -56,7 +56,7 @@ DI void wc_add(const WarpCounters& w, int i, int v) {   // all 32 lanes must cal
 }
 struct StepStats {
     int ncon, nefc, niter, nls;   // per lane, DEBUG only
-    int last_iter;                // Newton iterations of the most recent physics step: binning key of the next launch
+    int last_ls;                  // line-search evaluations of the most recent physics step: binning key of the next launch
 };
 
 // per-lane contact table (thread-local memory; only the first `nc` slots are ever touched).  Four float4 per contact
@@ -1163,7 +1163,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
     wc_add(wc, QG_C_NLS, leg == 0 ? nls : 0);
     wc_add(wc, QG_C_NACT, nact_last);
     if (DEBUG) { st.niter += (leg == 0) ? iter : 0; st.nls += nls; }
-    st.last_iter = iter;
+    st.last_ls = nls;
 
     // ---- sensors of this forward pass (pre-integration state, solver qacc)
     if (want_sensors) {
