@@ -42,6 +42,13 @@ WORKLOADS = {
 }
 
 
+def workload_config(name: str, envs: int, fs: int, max_time: float, desc: str) -> dict:
+    """The part of `config` that names the WORKLOAD: identical for our arm and the reference arm."""
+    return {"workload": desc, "envs_per_gpu": envs, "frame_skip": fs, "max_time_s": max_time,
+            "actions": "U(-1,1)^12 per env and env.step()", "auto_reset": "on fall (zaxis_z < 0) or time limit",
+            "rewards": "forward(qvel_x) - 0.1*sum(ctrl^2) + alive"}
+
+
 # ------------------------------------------------------------------------------------------ CPU arm
 def _cpu_worker(args):
     """One worker = one env stepped in a tight C loop (oracle port), like one SubprocVecEnv process
@@ -106,7 +113,11 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * t_tot / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "note": "CPU oracle port of mj_step for this model class (MuJoCo wheel not installable here); bounded sample"},
+        "config": dict(workload_config(a.workload, envs, fs, max_time, desc),
+                       note="same workload definition, BOUNDED SAMPLE: each of the %d host processes steps 1 env (the reference's "
+                            "SubprocVecEnv shape, train_quadruped.py:50) instead of envs_per_gpu envs; CPU oracle port of mj_step for "
+                            "this model class in float64 (the MuJoCo wheel is not installable in this image), so the ratio against "
+                            "this arm is 'vs our own CPU port', not 'vs MuJoCo'" % cores),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -177,11 +188,9 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the one JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION and above
-        if "QG_NCCL_DEBUG" in os.environ:
-            os.environ["NCCL_DEBUG"] = os.environ["QG_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)
+        # NCCL_DEBUG stays whatever the launcher set (the driver counts ranks from NCCL's INFO lines); its log goes to
+        # stderr so that stdout stays the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     envs, fs, max_time, desc = WORKLOADS[a.workload]
     if a.envs:
@@ -297,12 +306,17 @@ def run_ours(a):
         if not a.profile:
             _lib.lib().qg_fp32_peak(local, 4096, ctypes.byref(tf))
         launch_ms = float(np.mean(step_ms))
-        traffic = None   # dram bytes per launch from the committed ncu capture, scaled to this batch size
-        try:
-            pm = json.load(open(os.path.join(ROOT, "profiles", "r1_step_kernel_metrics.json")))
-            traffic = (pm["dram__bytes_read.sum"] + pm["dram__bytes_write.sum"]) / pm["envs"] * envs
-        except Exception:
-            pass
+        # dram bytes per launch: cannot be measured outside a profiler, so it is READ from the committed ncu capture of the
+        # same kernel (and scaled to this batch size) and labelled as such; null when no capture is committed
+        traffic, traffic_from = None, None
+        for cand in ("r2_step_kernel_metrics.json", "r1_step_kernel_metrics.json"):
+            try:
+                pm = json.load(open(os.path.join(ROOT, "profiles", cand)))
+                traffic = (pm["dram__bytes_read.sum"] + pm["dram__bytes_write.sum"]) / pm["envs"] * envs
+                traffic_from = "profiles/" + cand + " (ncu --set full of qg_step_kernel, per launch, scaled to envs_per_gpu)"
+                break
+            except Exception:
+                continue
         algo_bytes = 737.0 * envs  # 737 B per env.step() per env
         hbm_ach = algo_bytes / (launch_ms * 1e-3) / 1e9
         fp32_ach = fl * envs * fs / (launch_ms * 1e-3) / 1e12
@@ -312,19 +326,25 @@ def run_ours(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "envs_per_gpu": envs, "frame_skip": fs, "actions": "U(-1,1)^12 resident in HBM, %d tensors cycled" % NPOOL,
-                       "l2": "flushed (256 MiB write) between timed steps", "preroll_steps": PREROLL, "rewards": "forward(qvel_x) - 0.1*sum(ctrl^2) + alive",
-                       "parallelism": f"env-sharded x{world}, no data-path collective"},
+            "config": dict(workload_config(a.workload, envs, fs, max_time, desc),
+                           inputs="%d action tensors resident in HBM, cycled" % NPOOL,
+                           l2="flushed (256 MiB write) between timed steps", preroll_steps=PREROLL,
+                           parallelism=f"env-sharded x{world}, no data-path collective"),
             "clocks": clocks,
             "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": envs * 12 * 4,
                     "d2h_bytes_per_step": envs * (33 * 4 + 4 + 1)},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "note": "kernel is FP32-issue bound by design (SURVEY 8d); see roofline_fp32"},
-            "roofline_fp32": {"bound": "fp32-cuda-core", "achieved": fp32_ach, "peak": tf.value, "unit": "TFLOP/s",
-                              "frac": fp32_ach / tf.value if tf.value else None, "flops_per_physics_step": fl,
-                              "peak_source": "qg_fp32_peak FFMA chain measured in this run", "means_per_physics_step": means},
+            # the bounding roof of this path is FP32 CUDA-core issue (tiny per-env matrices, no dense contraction,
+            # 0.5 % of HBM): `roofline` is that object, the HBM figure rides along as `roofline_hbm`
+            "roofline": {"bound": "fp32-cuda-core", "achieved": fp32_ach, "peak": tf.value, "unit": "TFLOP/s",
+                         "frac": fp32_ach / tf.value if tf.value else None, "traffic": traffic, "traffic_from": traffic_from,
+                         "flops_per_physics_step": fl,
+                         "peak_source": "qg_fp32_peak: FFMA dependent chains on every SM, measured in this run (nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4)",
+                         "means_per_physics_step": means,
+                         "note": "achieved = SURVEY App. E flop model evaluated with the kernel's own counters x env-substeps per launch / mean launch time (CUDA events)"},
+            "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                             "traffic": traffic, "traffic_from": traffic_from, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
+                             "algorithmic_bytes_per_env_step": 737},
             "cpu_baseline": {"value": rp, "unit": UNIT, "cores": cores, "kind": "port",
                              "single_core_value": r1,
                              "sample": f"{cores} processes x 1 env x 3000 env.step() (frame_skip {fs}), random actions; oracle port, not MuJoCo"},

@@ -123,11 +123,18 @@ int qg_reset(qg_batch* b, const uint8_t* mask_dev, uint64_t seed, int random_yaw
 int qg_step(qg_batch* b, const float* action_dev, int frame_skip, float* obs_dev, float* reward_dev,
             float* terms_dev, uint8_t* terminated_dev, float* terminal_obs_dev, void* stream);
 
-/* Same call with HOST buffers: H2D of the actions, qg_step, D2H of obs / reward / terminated straight from / into
- * the caller's buffers (page-locked buffers are DMA-ed without staging), then a stream synchronise.
- * This is the end-to-end path. */
-int qg_step_host(qg_batch* b, const float* action_host, int frame_skip, float* obs_host,
-                 float* reward_host, uint8_t* terminated_host, void* stream);
+/* Same call with HOST buffers -- the end-to-end path.  The batch is cut into segments of contiguous environments
+ * (4 for >= 32,768 envs, 2 for >= 8,192, else 1), each on its own internal stream: H2D of the segment's actions, the
+ * step kernel over the segment, D2H of its obs / reward / terminated (and, if the pointers are given, of its reward terms
+ * [N,n_terms] and terminal observations [N,33]) straight from / into the caller's buffers (page-locked buffers are DMA-ed
+ * without staging), so the copies of one segment run under the kernels of the others.  Results are identical to
+ * qg_step's.  qg_step_host_async orders the work after the caller's earlier work on `stream` and returns without
+ * waiting; qg_host_wait blocks until the outputs are in the host buffers; qg_step_host = both. */
+int qg_step_host_async(qg_batch* b, const float* action_host, int frame_skip, float* obs_host, float* reward_host,
+                       float* terms_host, uint8_t* terminated_host, float* terminal_obs_host, void* stream);
+int qg_host_wait(qg_batch* b, void* stream);
+int qg_step_host(qg_batch* b, const float* action_host, int frame_skip, float* obs_host, float* reward_host,
+                 float* terms_host, uint8_t* terminated_host, float* terminal_obs_host, void* stream);
 
 /* state in MuJoCo's conventions: qpos [N,19], qvel [N,18], act [N,12], qacc_warmstart [N,18],
  * time [N] f64, ctrl [N,12]; any pointer may be NULL to skip that field. */
@@ -160,8 +167,12 @@ int qg_get_counters(qg_batch* b, qg_counters* out_host, int reset, void* stream)
 #define QG_WALK_NTERMS 11   /* WalkingQuadrupedEnv.reward_keys, walking_quad.py:331-350 */
 int qg_walk_enable(qg_batch* b, int window, double dt, double timestep, int frame_skip, double settling_time,
                    int random_controls, const double* sample_opts, const int* sample_has);
-/* reset() bookkeeping of WalkingQuadrupedEnv (walking_quad.py:96-126); hard != 0 also clears the state that
- * survives reset() in the reference (estimator, first control cost) and re-keys the command sampler. */
+/* options of control_inputs.sample for the NEXT resets (reset(options=...), walking_quad.py:100-103,121-122):
+ * same layout as in qg_walk_enable; NULL pointers = the sampler's defaults (speed U(0,1), angles U(-pi,pi)). */
+int qg_walk_set_sample_options(qg_batch* b, const double* sample_opts, const int* sample_has);
+/* reset() bookkeeping of WalkingQuadrupedEnv (walking_quad.py:96-126); the command sampler is keyed on
+ * (seed, env_offset + env, episode) from THIS call; hard != 0 also clears the state that survives reset() in the
+ * reference (estimator, first control cost) and restarts the episode counters. */
 int qg_walk_reset(qg_batch* b, const uint8_t* mask_dev, int hard, uint64_t seed, long long env_offset, void* stream);
 /* set_velocity_speed_alpha + set_orientation (control_inputs.py:36-51): [N,3] = speed, alpha, theta (float64) */
 int qg_walk_set_commands(qg_batch* b, const double* speed_alpha_theta_dev, const uint8_t* mask_dev, void* stream);
@@ -181,7 +192,9 @@ int qg_walk_step(qg_batch* b, float* obs_dev, const float* ctrl_dev, const uint8
  * 26 values per frame (gyro, accel, Madgwick-filter Euler angles, body_vel xy, ctrl, command velocity xy, heading
  * angle), FIFO-stacked over obs_window frames -> stacked_dev [N, 26*obs_window] f32, oldest frame first.
  * Dt = timestep*frame_skip (po_walking_quad.py:18), beta = Madgwick IMU gain (ahrs default 0.033).
- * qg_po_observe(is_reset_call = 0) runs after qg_step + qg_walk_step and before the masked qg_reset of a step;
+ * Call order of one step: qg_step, then qg_po_observe(is_reset_call = 0), then qg_walk_step, then the masked qg_reset
+ * (qg_walk_step zeroes the observation of terminated envs and resamples their commands, so the frame must be built
+ * before it, exactly as the reference builds it inside QuadrupedEnv.step, quadruped.py:167);
  * sensordata_dev is that step's sensordata (the terminal one for terminated envs).  is_reset_call = 1 fills the
  * stack of the masked envs (terminated_dev as mask, NULL = all) with the reset frame (po_walking_quad.py:59-70). */
 #define QG_PO_FRAME 26

@@ -23,8 +23,8 @@ TERM_IDS = {
 SYMBOLS = [
     "qg_last_error", "qg_version", "qg_model_load", "qg_model_destroy", "qg_model_info", "qg_batch_create",
     "qg_batch_destroy", "qg_batch_num_envs", "qg_set_options", "qg_set_reward_table", "qg_reset", "qg_step",
-    "qg_step_host", "qg_get_state", "qg_set_state", "qg_debug_step", "qg_get_counters", "qg_launch_count",
-    "qg_fp32_peak", "qg_walk_enable", "qg_walk_reset", "qg_walk_set_commands", "qg_walk_get_commands", "qg_walk_step",
+    "qg_step_host", "qg_step_host_async", "qg_host_wait", "qg_get_state", "qg_set_state", "qg_debug_step", "qg_get_counters", "qg_launch_count",
+    "qg_fp32_peak", "qg_walk_enable", "qg_walk_set_sample_options", "qg_walk_reset", "qg_walk_set_commands", "qg_walk_get_commands", "qg_walk_step",
     "qg_po_enable", "qg_po_observe",
 ]
 
@@ -76,7 +76,9 @@ def lib():
     L.qg_set_reward_table.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.qg_reset.argtypes = [vp, u8p, C.c_uint64, i32, C.c_longlong, vp]
     L.qg_step.argtypes = [vp, f32p, i32, f32p, f32p, f32p, u8p, f32p, vp]
-    L.qg_step_host.argtypes = [vp, f32p, i32, f32p, f32p, u8p, vp]
+    L.qg_step_host.argtypes = [vp, f32p, i32, f32p, f32p, f32p, u8p, f32p, vp]
+    L.qg_step_host_async.argtypes = [vp, f32p, i32, f32p, f32p, f32p, u8p, f32p, vp]
+    L.qg_host_wait.argtypes = [vp, vp]
     L.qg_get_state.argtypes = [vp, f32p, f32p, f32p, f32p, f64p, f32p, vp]
     L.qg_set_state.argtypes = [vp, f32p, f32p, f32p, f32p, f64p, f32p, vp]
     L.qg_debug_step.argtypes = [vp, f32p, f32p, f32p, f32p, f32p, vp, f32p, vp]
@@ -84,6 +86,7 @@ def lib():
     L.qg_launch_count.restype = C.c_ulonglong
     L.qg_fp32_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]
     L.qg_walk_enable.argtypes = [vp, i32, C.c_double, C.c_double, i32, C.c_double, i32, C.POINTER(C.c_double), C.POINTER(i32)]
+    L.qg_walk_set_sample_options.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i32)]
     L.qg_walk_reset.argtypes = [vp, u8p, i32, C.c_uint64, C.c_longlong, vp]
     L.qg_walk_set_commands.argtypes = [vp, f64p, u8p, vp]
     L.qg_walk_get_commands.argtypes = [vp, f64p, f64p, f64p, f64p, f64p, f64p, vp]

@@ -40,6 +40,17 @@ struct qg_model {
     double timestep;
 };
 
+// One launch domain of the step kernel: the whole batch (device path) or one segment of the pipelined host path.
+// Each has its own chunk counter, binning histogram and slice of the slot -> env permutation.
+struct Segment {
+    int env0 = 0, cnt = 0;
+    int* d_chunk = nullptr;       // [2] chunk counter of the persistent step kernel, blocks-done counter
+    int* d_bin_count = nullptr;   // [2][QG_NBINS] = counts, cursors
+    bool perm_valid = false;
+    cudaStream_t st = nullptr;    // host path only
+    cudaEvent_t done = nullptr;
+};
+
 struct qg_batch {
     int n, device;
     QgModelC* d_model;
@@ -51,18 +62,21 @@ struct qg_batch {
     size_t smem;
     int num_sms, cone;
     // environment binning (slot -> env permutation refreshed after every step launch)
-    int *d_perm, *d_bin_count;   // d_bin_count: [2][QG_NBINS] = counts, cursors
-    unsigned char* d_bin_key;
-    int* d_chunk;   // [2] chunk counter of the persistent step kernel, blocks-done counter
-    bool perm_valid, binning;
+    int* d_perm;                 // [N] slot -> env; the full-batch launch and the host segments lay it out differently
+    unsigned char* d_bin_key;    // [N] key the step kernel leaves for the next launch's binning
+    bool binning;
+    Segment full;                // the device path's launch domain
+    std::vector<Segment> segs;   // the host path's (qg_step_host), created on first use
+    int perm_layout;             // 0 = d_perm holds one permutation of the batch, 1 = one permutation per host segment
+    cudaEvent_t ev_start;
     // device staging for the host-buffer path (qg_step_host)
-    float *d_act, *d_obs, *d_rew;
+    float *d_act, *d_obs, *d_rew, *d_terms, *d_tobs;
     unsigned char* d_term;
     // WalkingQuadrupedEnv reward stack (qg_walk_*)
     bool walk_on;
     QgWalkState walk;
     QgWalkOpts wopts;
-    std::vector<void*> walk_allocs;
+    std::vector<void*> walk_allocs, po_allocs;
     bool po_on;
     QgPoState po;
 };
@@ -467,6 +481,27 @@ static void default_opts(const qg_model* m, QgStepOpts& o) {
     o.n_terms = 0;
 }
 
+static int batch_create_impl(const qg_model* m, int n_envs, int device, qg_batch* b);
+static int segment_alloc(Segment& sg, bool with_stream) {
+    CUDA_OK(cudaMalloc(&sg.d_bin_count, sizeof(int) * 2 * QG_NBINS));
+    CUDA_OK(cudaMalloc(&sg.d_chunk, 2 * sizeof(int)));
+    CUDA_OK(cudaMemset(sg.d_chunk, 0, 2 * sizeof(int)));
+    sg.perm_valid = false;
+    if (with_stream) {
+        CUDA_OK(cudaStreamCreateWithFlags(&sg.st, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&sg.done, cudaEventDisableTiming));
+    }
+    return QG_OK;
+}
+static void segment_free(Segment& sg) {
+    cudaFree(sg.d_bin_count); cudaFree(sg.d_chunk);
+    if (sg.st) cudaStreamDestroy(sg.st);
+    if (sg.done) cudaEventDestroy(sg.done);
+    sg = Segment();
+}
+static int reset_impl(qg_batch* b, const uint8_t* mask_dev, uint64_t seed, int random_yaw, long long env_offset,
+                      int clear_env_state, cudaStream_t st);
+
 extern "C" int qg_batch_create(const qg_model* m, int n_envs, int device, qg_batch** out) {
     if (!m || !out || n_envs <= 0) return fail(QG_EINVAL, "bad arguments to qg_batch_create");
     int ndev = 0;
@@ -476,6 +511,16 @@ extern "C" int qg_batch_create(const qg_model* m, int n_envs, int device, qg_bat
     if (device < 0 || device >= ndev) return fail(QG_EINVAL, "device %d out of range (%d devices)", device, ndev);
     CUDA_OK(cudaSetDevice(device));
     qg_batch* b = new qg_batch();
+    int rc = batch_create_impl(m, n_envs, device, b);
+    if (rc) { qg_batch_destroy(b); return rc; }   // frees whatever was allocated before the failure
+    *out = b;
+    return QG_OK;
+}
+
+static int batch_create_impl(const qg_model* m, int n_envs, int device, qg_batch* b) {
+    b->d_model = nullptr; b->d_verts = nullptr; b->d_adj4 = b->d_cadj4 = nullptr; b->d_state = nullptr; b->d_ctr = nullptr;
+    b->d_perm = nullptr; b->d_bin_key = nullptr; b->perm_layout = 0; b->ev_start = nullptr;
+    b->d_terms = b->d_tobs = nullptr;
     b->walk_on = false;
     b->po_on = false;
     memset(&b->po, 0, sizeof b->po);
@@ -505,19 +550,19 @@ extern "C" int qg_batch_create(const qg_model* m, int n_envs, int device, qg_bat
     CUDA_OK(cudaMemset(b->d_state, 0, sizeof(float4) * (size_t)QG_NPLANE * n_envs));
     CUDA_OK(cudaMemset(b->d_ctr, 0, sizeof(QgCounters)));
     CUDA_OK(cudaMalloc(&b->d_perm, sizeof(int) * n_envs));
-    CUDA_OK(cudaMalloc(&b->d_bin_count, sizeof(int) * 2 * QG_NBINS));
     CUDA_OK(cudaMalloc(&b->d_bin_key, n_envs));
     CUDA_OK(cudaMemset(b->d_bin_key, 0, n_envs));
-    CUDA_OK(cudaMalloc(&b->d_chunk, 2 * sizeof(int)));
-    CUDA_OK(cudaMemset(b->d_chunk, 0, 2 * sizeof(int)));
-    b->perm_valid = false;
+    b->full.env0 = 0;
+    b->full.cnt = n_envs;
+    { int rc0 = segment_alloc(b->full, false); if (rc0) return rc0; }
     // environment binning (slot -> env permutation refreshed every step from the last physics step's per-leg contact count
     // and line-search evaluations): measured -2 % step time at 65,536 envs, for 2 extra tiny launches per step.  On by default
     // only for batches large enough to pay for those; QG_BINNING=0/1 overrides.  Results per environment do not depend
     // on the slot (test_env_binning_does_not_change_results).
     b->binning = n_envs >= 32768;
     if (const char* ev = getenv("QG_BINNING")) b->binning = atoi(ev) != 0;   // tests / experiments
-    b->smem = ((sizeof(QgModelC) + 15) & ~size_t(15)) + sizeof(float4) * nv + sizeof(float) * (QG_QR_SLOTS * 32) * (QG_BLOCK / 32);
+    b->smem = ((sizeof(QgModelC) + 15) & ~size_t(15)) + sizeof(float4) * nv + sizeof(float) * (QG_QR_SLOTS * 32) * (QG_BLOCK / 32) +
+              sizeof(float) * (SB_NWORDS * (QG_BLOCK / 4) + SL_NWORDS * QG_BLOCK);   // + the block's resident state
     CUDA_OK(cudaFuncSetAttribute(qg_step_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
     CUDA_OK(cudaFuncSetAttribute(qg_step_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
     CUDA_OK(cudaFuncSetAttribute(qg_step_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
@@ -528,8 +573,7 @@ extern "C" int qg_batch_create(const qg_model* m, int n_envs, int device, qg_bat
         cudaFuncSetAttribute(qg_step_kernel<false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     }
     b->cone = m->c.cone;
-    *out = b;
-    int rc = qg_reset(b, nullptr, 0, 0, 0, nullptr);
+    int rc = reset_impl(b, nullptr, 0, 0, 0, 1, nullptr);
     if (rc) return rc;
     CUDA_OK(cudaDeviceSynchronize());
     return QG_OK;
@@ -539,9 +583,13 @@ extern "C" void qg_batch_destroy(qg_batch* b) {
     if (!b) return;
     cudaSetDevice(b->device);
     cudaFree(b->d_model); cudaFree(b->d_verts); cudaFree(b->d_adj4); cudaFree(b->d_cadj4);
-    cudaFree(b->d_state); cudaFree(b->d_ctr); cudaFree(b->d_perm); cudaFree(b->d_bin_count); cudaFree(b->d_bin_key); cudaFree(b->d_chunk);
-    cudaFree(b->d_act); cudaFree(b->d_obs); cudaFree(b->d_rew); cudaFree(b->d_term);
+    cudaFree(b->d_state); cudaFree(b->d_ctr); cudaFree(b->d_perm); cudaFree(b->d_bin_key);
+    segment_free(b->full);
+    for (Segment& sg : b->segs) segment_free(sg);
+    if (b->ev_start) cudaEventDestroy(b->ev_start);
+    cudaFree(b->d_act); cudaFree(b->d_obs); cudaFree(b->d_rew); cudaFree(b->d_term); cudaFree(b->d_terms); cudaFree(b->d_tobs);
     for (void* p : b->walk_allocs) cudaFree(p);
+    for (void* p : b->po_allocs) cudaFree(p);
     delete b;
 }
 
@@ -572,55 +620,80 @@ extern "C" int qg_set_reward_table(qg_batch* b, int n_terms, const int* term_ids
     return QG_OK;
 }
 
-static inline int nblocks(int n_envs) { return (4 * n_envs + QG_BLOCK - 1) / QG_BLOCK; }
+static inline int nblocks(int n_envs) { return (4 * n_envs + 255) / 256; }   // helper kernels: 256 threads, 4 per env
 
 // step-kernel block size: QG_BLOCK (warps of a block share instruction-cache fills through the block barriers);
 // one halving for small batches whose grid would leave SMs without a block
-static int step_block(const qg_batch* b) {
+static int step_block(const qg_batch* b, int n_envs) {
     int blk = QG_BLOCK;
     static const int forced = getenv("QG_STEP_BLOCK") ? atoi(getenv("QG_STEP_BLOCK")) : 0;   // tuning experiments
     if (forced >= 32 && forced <= QG_BLOCK && forced % 32 == 0) return forced;
-    if (blk > 128 && (4 * b->n + blk - 1) / blk < b->num_sms) blk >>= 1;
+    if (blk > 128 && (4 * n_envs + blk - 1) / blk < b->num_sms) blk >>= 1;
     return blk;
+}
+
+// clear_env_state: also zero the episode counter and the reward memory (first control cost) -- batch creation only;
+// a user-level reset() keeps both, like the reference (walking_quad.py:106-115 never resets previous_ctrl_cost)
+static int reset_impl(qg_batch* b, const uint8_t* mask_dev, uint64_t seed, int random_yaw, long long env_offset,
+                      int clear_env_state, cudaStream_t st) {
+    b->opts.seed = seed;
+    b->opts.random_yaw = random_yaw;
+    b->opts.env_offset = env_offset;
+    qg_reset_kernel<<<nblocks(b->n), 256, 0, st>>>(b->d_model, b->d_state, b->n, mask_dev, b->opts, clear_env_state);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return QG_OK;
 }
 
 extern "C" int qg_reset(qg_batch* b, const uint8_t* mask_dev, uint64_t seed, int random_yaw, long long env_offset,
                         void* stream) {
     if (!b) return fail(QG_EINVAL, "batch is NULL");
     CUDA_OK(cudaSetDevice(b->device));
-    b->opts.seed = seed;
-    b->opts.random_yaw = random_yaw;
-    b->opts.env_offset = env_offset;
-    qg_reset_kernel<<<nblocks(b->n), QG_BLOCK, 0, (cudaStream_t)stream>>>(b->d_model, b->d_state, b->n, mask_dev, b->opts,
-                                                                           mask_dev == nullptr ? 0 : 0);
+    return reset_impl(b, mask_dev, seed, random_yaw, env_offset, 0, (cudaStream_t)stream);
+}
+
+// One launch of the step kernel over the environments of `sg` (all I/O pointers are whole-batch arrays indexed by the
+// absolute env id).
+template <bool DEBUG>
+static int launch_step(qg_batch* b, Segment& sg, const float* action, int clip, int frame_skip, float* obs, float* reward,
+                       float* terms, unsigned char* terminated, float* terminal_obs, QgDebugOut dbg, cudaStream_t st) {
+    const int blk = step_block(b, sg.cnt);
+    auto kern = b->cone ? qg_step_kernel<DEBUG, 1> : qg_step_kernel<DEBUG, 0>;
+    const int nchunks = (4 * sg.cnt + blk - 1) / blk;
+    const int resident = b->num_sms * QG_MINBLOCKS * (QG_BLOCK / blk);   // register file: QG_BLOCK * QG_MINBLOCKS threads per SM
+    kern<<<nchunks < resident ? nchunks : resident, blk, b->smem, st>>>(b->d_model, b->d_verts, b->d_adj4, b->d_cadj4,
+                                                                     b->d_state, b->n, action, clip, frame_skip, obs, reward,
+                                                                     terms, terminated, terminal_obs, b->opts, b->d_ctr, dbg,
+                                                                     sg.perm_valid ? b->d_perm + sg.env0 : nullptr,
+                                                                     b->binning ? b->d_bin_key : nullptr, sg.d_chunk, nchunks,
+                                                                     sg.env0, sg.cnt);
     g_launches++;
     CUDA_OK(cudaGetLastError());
     return QG_OK;
 }
 
-template <bool DEBUG>
-static int launch_step(qg_batch* b, const float* action, int clip, int frame_skip, float* obs, float* reward, float* terms,
-                       unsigned char* terminated, float* terminal_obs, QgDebugOut dbg, cudaStream_t st) {
-    const int blk = step_block(b);
-    auto kern = b->cone ? qg_step_kernel<DEBUG, 1> : qg_step_kernel<DEBUG, 0>;
-    const int nchunks = (4 * b->n + blk - 1) / blk;
-    const int resident = b->num_sms * (QG_BLOCK / blk);   // 255 registers: QG_BLOCK threads per SM
-    kern<<<nchunks < resident ? nchunks : resident, blk, b->smem, st>>>(b->d_model, b->d_verts, b->d_adj4, b->d_cadj4,
-                                                                     b->d_state, b->n, action, clip, frame_skip, obs, reward,
-                                                                     terms, terminated, terminal_obs, b->opts, b->d_ctr, dbg,
-                                                                     b->perm_valid ? b->d_perm : nullptr, b->binning ? b->d_bin_key : nullptr,
-                                                                     b->d_chunk, nchunks);
-    g_launches++;
-    CUDA_OK(cudaGetLastError());
-    if (b->binning) {   // next launch's slot -> env map: group environments by last-step solver effort
-        CUDA_OK(cudaMemsetAsync(b->d_bin_count, 0, sizeof(int) * 2 * QG_NBINS, st));
-        qg_bin_hist_kernel<<<64, 256, 0, st>>>(b->d_bin_key, b->n, b->d_bin_count);
-        qg_bin_scatter_kernel<<<(b->n + 255) / 256, 256, 0, st>>>(b->d_bin_key, b->n, b->d_bin_count, b->d_bin_count + QG_NBINS, b->d_perm);
+// the two binning kernels that prepare the segment's next launch (slot -> env map: environments grouped by the solver
+// effort of their last physics step)
+static int launch_binning(qg_batch* b, Segment& sg, cudaStream_t st) {
+    if (b->binning) {
+        CUDA_OK(cudaMemsetAsync(sg.d_bin_count, 0, sizeof(int) * 2 * QG_NBINS, st));
+        qg_bin_hist_kernel<<<64, 256, 0, st>>>(b->d_bin_key + sg.env0, sg.cnt, sg.d_bin_count);
+        qg_bin_scatter_kernel<<<(sg.cnt + 255) / 256, 256, 0, st>>>(b->d_bin_key + sg.env0, sg.cnt, sg.d_bin_count,
+                                                                   sg.d_bin_count + QG_NBINS, b->d_perm + sg.env0, sg.env0);
         g_launches += 2;
         CUDA_OK(cudaGetLastError());
-        b->perm_valid = true;
+        sg.perm_valid = true;
     }
     return QG_OK;
+}
+
+// d_perm is laid out either as one permutation of the batch (device path) or as one per host segment: switching paths
+// drops the stale permutations (the next launch runs in env order and rebuilds them)
+static void use_perm_layout(qg_batch* b, int layout) {
+    if (b->perm_layout == layout) return;
+    b->perm_layout = layout;
+    b->full.perm_valid = false;
+    for (Segment& sg : b->segs) sg.perm_valid = false;
 }
 
 extern "C" int qg_step(qg_batch* b, const float* action_dev, int frame_skip, float* obs_dev, float* reward_dev,
@@ -630,12 +703,46 @@ extern "C" int qg_step(qg_batch* b, const float* action_dev, int frame_skip, flo
     CUDA_OK(cudaSetDevice(b->device));
     QgDebugOut dbg;
     memset(&dbg, 0, sizeof dbg);
-    return launch_step<false>(b, action_dev, 1, frame_skip, obs_dev, reward_dev, terms_dev, terminated_dev,
-                              terminal_obs_dev, dbg, (cudaStream_t)stream);
+    use_perm_layout(b, 0);
+    int rc = launch_step<false>(b, b->full, action_dev, 1, frame_skip, obs_dev, reward_dev, terms_dev, terminated_dev,
+                                terminal_obs_dev, dbg, (cudaStream_t)stream);
+    return rc ? rc : launch_binning(b, b->full, (cudaStream_t)stream);
 }
 
-extern "C" int qg_step_host(qg_batch* b, const float* action_host, int frame_skip, float* obs_host, float* reward_host,
-                            uint8_t* terminated_host, void* stream) {
+// Host-buffer path, pipelined: the batch is cut into segments of contiguous environments, each with its own stream:
+//   H2D(actions of segment s) -> step kernel over segment s -> D2H(outputs of segment s).
+// The copies of one segment run under the kernels of the others (the persistent kernel of segment s+1 takes over the
+// SMs one by one as the blocks of segment s run out of chunks, so the cut costs no wave efficiency); only the first
+// segment's H2D and the last segment's D2H are exposed.  Results do not depend on the segmentation (environments are
+// independent, the binning permutation stays inside a segment).
+static int host_segments(qg_batch* b) {
+    if (!b->segs.empty()) return QG_OK;
+    int nseg = b->n >= 32768 ? 4 : (b->n >= 8192 ? 2 : 1);
+    if (const char* ev = getenv("QG_HOST_SEGMENTS")) nseg = atoi(ev) > 0 ? atoi(ev) : nseg;   // tuning experiments
+    if (nseg > b->n) nseg = b->n;
+    // Only the first segment's H2D and the last segment's D2H are exposed, so with 4 or more segments the two outer
+    // ones get half the share of an inner one.  Boundaries on multiples of 64 environments (whole chunks, 16-byte
+    // aligned flag slices).
+    const int shares = nseg >= 4 ? 2 * nseg - 2 : nseg;
+    int e0 = 0;
+    for (int s = 0; s < nseg && e0 < b->n; ++s) {
+        const int w = (nseg >= 4 && s > 0 && s < nseg - 1) ? 2 : 1;
+        int c = (int)(((long long)b->n * w / shares + 63) / 64 * 64);
+        if (s == nseg - 1 || e0 + c > b->n) c = b->n - e0;
+        Segment sg;
+        sg.env0 = e0;
+        sg.cnt = c;
+        int rc = segment_alloc(sg, true);
+        b->segs.push_back(sg);   // pushed even on failure so that qg_batch_destroy frees what was allocated
+        if (rc) return rc;
+        e0 += c;
+    }
+    CUDA_OK(cudaEventCreateWithFlags(&b->ev_start, cudaEventDisableTiming));
+    return QG_OK;
+}
+
+extern "C" int qg_step_host_async(qg_batch* b, const float* action_host, int frame_skip, float* obs_host, float* reward_host,
+                                  float* terms_host, uint8_t* terminated_host, float* terminal_obs_host, void* stream) {
     if (!b || !action_host || !obs_host || !reward_host || !terminated_host) return fail(QG_EINVAL, "qg_step_host: NULL argument");
     if (frame_skip < 1) return fail(QG_EINVAL, "frame_skip must be >= 1");
     CUDA_OK(cudaSetDevice(b->device));
@@ -647,18 +754,61 @@ extern "C" int qg_step_host(qg_batch* b, const float* action_host, int frame_ski
         CUDA_OK(cudaMalloc(&b->d_rew, n * sizeof(float)));
         CUDA_OK(cudaMalloc(&b->d_term, n));
     }
-    // the copies run straight from / into the caller's buffers: page-locked buffers (cudaHostAlloc, torch pin_memory)
-    // are DMA-ed asynchronously, pageable ones go through the driver's staging
-    CUDA_OK(cudaMemcpyAsync(b->d_act, action_host, n * 12 * sizeof(float), cudaMemcpyHostToDevice, st));
+    const int nt = b->opts.n_terms;
+    if (terms_host && nt > 0 && !b->d_terms) CUDA_OK(cudaMalloc(&b->d_terms, n * QG_MAX_TERMS * sizeof(float)));
+    if (terminal_obs_host && !b->d_tobs) CUDA_OK(cudaMalloc(&b->d_tobs, n * 33 * sizeof(float)));
+    int rc = host_segments(b);
+    if (rc) return rc;
+    use_perm_layout(b, 1);
     QgDebugOut dbg;
     memset(&dbg, 0, sizeof dbg);
-    int rc = launch_step<false>(b, b->d_act, 1, frame_skip, b->d_obs, b->d_rew, nullptr, b->d_term, nullptr, dbg, st);
-    if (rc) return rc;
-    CUDA_OK(cudaMemcpyAsync(obs_host, b->d_obs, n * 33 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(reward_host, b->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(terminated_host, b->d_term, n, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaStreamSynchronize(st));
+    float* d_terms = (terms_host && nt > 0) ? b->d_terms : nullptr;
+    float* d_tobs = terminal_obs_host ? b->d_tobs : nullptr;
+    CUDA_OK(cudaEventRecord(b->ev_start, st));   // the segments start after the caller's earlier work on `stream`
+    // the copies run straight from / into the caller's buffers: page-locked buffers (cudaHostAlloc, torch pin_memory)
+    // are DMA-ed asynchronously, pageable ones go through the driver's staging
+    for (Segment& sg : b->segs) {
+        const size_t e0 = sg.env0, c = sg.cnt;
+        CUDA_OK(cudaStreamWaitEvent(sg.st, b->ev_start, 0));
+        CUDA_OK(cudaMemcpyAsync(b->d_act + e0 * 12, action_host + e0 * 12, c * 12 * sizeof(float), cudaMemcpyHostToDevice, sg.st));
+        rc = launch_step<false>(b, sg, b->d_act, 1, frame_skip, b->d_obs, b->d_rew, d_terms, b->d_term, d_tobs, dbg, sg.st);
+        if (rc) return rc;
+    }
+    // D2H in segment order on each segment's stream (issued after ALL launches: a copy queued before a later segment's
+    // H2D would hold the copy engine's queue while its kernel runs)
+    for (Segment& sg : b->segs) {
+        const size_t e0 = sg.env0, c = sg.cnt;
+        CUDA_OK(cudaMemcpyAsync(obs_host + e0 * 33, b->d_obs + e0 * 33, c * 33 * sizeof(float), cudaMemcpyDeviceToHost, sg.st));
+        CUDA_OK(cudaMemcpyAsync(reward_host + e0, b->d_rew + e0, c * sizeof(float), cudaMemcpyDeviceToHost, sg.st));
+        CUDA_OK(cudaMemcpyAsync(terminated_host + e0, b->d_term + e0, c, cudaMemcpyDeviceToHost, sg.st));
+        if (d_terms) CUDA_OK(cudaMemcpyAsync(terms_host + e0 * nt, d_terms + e0 * nt, c * nt * sizeof(float), cudaMemcpyDeviceToHost, sg.st));
+        if (d_tobs) CUDA_OK(cudaMemcpyAsync(terminal_obs_host + e0 * 33, d_tobs + e0 * 33, c * 33 * sizeof(float), cudaMemcpyDeviceToHost, sg.st));
+        CUDA_OK(cudaEventRecord(sg.done, sg.st));
+        CUDA_OK(cudaStreamWaitEvent(st, sg.done, 0));   // later work on the caller's stream sees the finished step
+    }
+    // binning for the next step AFTER the copies in stream order: the tiny kernels cannot start while the next segment's
+    // persistent blocks hold every SM's registers, and the D2H must not wait for them
+    for (Segment& sg : b->segs) {
+        rc = launch_binning(b, sg, sg.st);
+        if (rc) return rc;
+    }
     return QG_OK;
+}
+
+extern "C" int qg_host_wait(qg_batch* b, void* stream) {
+    if (!b) return fail(QG_EINVAL, "batch is NULL");
+    CUDA_OK(cudaSetDevice(b->device));
+    // the caller's stream already waits for every segment's `done` event: one blocking call
+    CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    return QG_OK;
+}
+
+extern "C" int qg_step_host(qg_batch* b, const float* action_host, int frame_skip, float* obs_host, float* reward_host,
+                            float* terms_host, uint8_t* terminated_host, float* terminal_obs_host, void* stream) {
+    int rc = qg_step_host_async(b, action_host, frame_skip, obs_host, reward_host, terms_host, terminated_host,
+                                terminal_obs_host, stream);
+    if (rc) return rc;
+    return qg_host_wait(b, stream);
 }
 
 extern "C" int qg_debug_step(qg_batch* b, const float* ctrl_dev, float* qacc_dev, float* qacc_smooth_dev,
@@ -676,8 +826,10 @@ extern "C" int qg_debug_step(qg_batch* b, const float* ctrl_dev, float* qacc_dev
     QgStepOpts saved = b->opts;
     b->opts.auto_reset = 0;
     b->opts.n_terms = 0;
-    int rc = launch_step<true>(b, ctrl_dev, 0, 1, scratch, scratch + n * 33, nullptr, (unsigned char*)(scratch + n * 34),
+    use_perm_layout(b, 0);
+    int rc = launch_step<true>(b, b->full, ctrl_dev, 0, 1, scratch, scratch + n * 33, nullptr, (unsigned char*)(scratch + n * 34),
                                nullptr, dbg, st);
+    if (!rc) rc = launch_binning(b, b->full, st);
     b->opts = saved;
     cudaError_t e = cudaStreamSynchronize(st);
     cudaFree(scratch);
@@ -690,7 +842,7 @@ extern "C" int qg_get_state(qg_batch* b, float* qpos_dev, float* qvel_dev, float
                             double* time_dev, float* ctrl_dev, void* stream) {
     if (!b) return fail(QG_EINVAL, "batch is NULL");
     CUDA_OK(cudaSetDevice(b->device));
-    qg_get_state_kernel<<<nblocks(b->n), QG_BLOCK, 0, (cudaStream_t)stream>>>(b->d_state, b->n, qpos_dev, qvel_dev, act_dev,
+    qg_get_state_kernel<<<nblocks(b->n), 256, 0, (cudaStream_t)stream>>>(b->d_state, b->n, qpos_dev, qvel_dev, act_dev,
                                                                                warm_dev, time_dev, ctrl_dev);
     g_launches++;
     CUDA_OK(cudaGetLastError());
@@ -701,7 +853,7 @@ extern "C" int qg_set_state(qg_batch* b, const float* qpos_dev, const float* qve
                             const float* warm_dev, const double* time_dev, const float* ctrl_dev, void* stream) {
     if (!b) return fail(QG_EINVAL, "batch is NULL");
     CUDA_OK(cudaSetDevice(b->device));
-    qg_set_state_kernel<<<nblocks(b->n), QG_BLOCK, 0, (cudaStream_t)stream>>>(b->d_state, b->n, qpos_dev, qvel_dev, act_dev,
+    qg_set_state_kernel<<<nblocks(b->n), 256, 0, (cudaStream_t)stream>>>(b->d_state, b->n, qpos_dev, qvel_dev, act_dev,
                                                                                warm_dev, time_dev, ctrl_dev);
     g_launches++;
     CUDA_OK(cudaGetLastError());
@@ -753,10 +905,24 @@ extern "C" int qg_fp32_peak(int device, int iters, double* tflops_out) {
 
 // ------------------------------------------------------------------------------------------ walking env
 template <typename T>
-static int walk_alloc(qg_batch* b, T** p, size_t count) {
+static int walk_alloc(std::vector<void*>& owner, T** p, size_t count) {
     CUDA_OK(cudaMalloc(p, sizeof(T) * count));
     CUDA_OK(cudaMemset(*p, 0, sizeof(T) * count));
-    b->walk_allocs.push_back(*p);
+    owner.push_back(*p);
+    return QG_OK;
+}
+
+extern "C" int qg_walk_set_sample_options(qg_batch* b, const double* sample_opts, const int* sample_has) {
+    if (!b) return fail(QG_EINVAL, "batch is NULL");
+    QgWalkOpts& o = b->wopts;
+    o.min_speed = sample_opts ? sample_opts[0] : 0.0;
+    o.max_speed = sample_opts ? sample_opts[1] : 1.0;
+    o.fixed_heading = sample_opts ? sample_opts[2] : 0.0;
+    o.fixed_velocity_angle = sample_opts ? sample_opts[3] : 0.0;
+    o.fixed_speed = sample_opts ? sample_opts[4] : 0.0;
+    o.has_heading = (sample_opts && sample_has) ? sample_has[0] : 0;
+    o.has_velocity_angle = (sample_opts && sample_has) ? sample_has[1] : 0;
+    o.has_speed = (sample_opts && sample_has) ? sample_has[2] : 0;
     return QG_OK;
 }
 
@@ -770,37 +936,38 @@ extern "C" int qg_walk_enable(qg_batch* b, int window, double dt, double timeste
     const size_t n = b->n;
     W.n = b->n; W.window = window; W.dt = dt; W.timestep = timestep; W.frame_skip = frame_skip; W.ema_alpha = 0.80;
     int rc = 0;
-    rc |= walk_alloc(b, &W.velocity, 3 * n); rc |= walk_alloc(b, &W.heading, 3 * n); rc |= walk_alloc(b, &W.global_velocity, 3 * n);
-    rc |= walk_alloc(b, &W.ideal_position, 3 * n); rc |= walk_alloc(b, &W.prev_derive, n); rc |= walk_alloc(b, &W.first_ctrl_cost, n);
-    rc |= walk_alloc(b, &W.prev_ctrl, 12 * n); rc |= walk_alloc(b, &W.signal_ring, (size_t)window * 12 * n);
-    rc |= walk_alloc(b, &W.cross_ring, (size_t)window * 12 * n); rc |= walk_alloc(b, &W.cross_count, 12 * n);
-    rc |= walk_alloc(b, &W.prev_sample, 12 * n); rc |= walk_alloc(b, &W.f_est, 12 * n); rc |= walk_alloc(b, &W.a_est, 12 * n);
-    rc |= walk_alloc(b, &W.prev_sign, 12 * n); rc |= walk_alloc(b, &W.buffer_index, n); rc |= walk_alloc(b, &W.sample_count, n);
-    rc |= walk_alloc(b, &W.flags, n); rc |= walk_alloc(b, &W.episode, n);
+    rc |= walk_alloc(b->walk_allocs, &W.velocity, 3 * n); rc |= walk_alloc(b->walk_allocs, &W.heading, 3 * n); rc |= walk_alloc(b->walk_allocs, &W.global_velocity, 3 * n);
+    rc |= walk_alloc(b->walk_allocs, &W.ideal_position, 3 * n); rc |= walk_alloc(b->walk_allocs, &W.prev_derive, n); rc |= walk_alloc(b->walk_allocs, &W.first_ctrl_cost, n);
+    rc |= walk_alloc(b->walk_allocs, &W.prev_ctrl, 12 * n); rc |= walk_alloc(b->walk_allocs, &W.signal_ring, (size_t)window * 12 * n);
+    rc |= walk_alloc(b->walk_allocs, &W.cross_ring, (size_t)window * 12 * n); rc |= walk_alloc(b->walk_allocs, &W.cross_count, 12 * n);
+    rc |= walk_alloc(b->walk_allocs, &W.prev_sample, 12 * n); rc |= walk_alloc(b->walk_allocs, &W.f_est, 12 * n); rc |= walk_alloc(b->walk_allocs, &W.a_est, 12 * n);
+    rc |= walk_alloc(b->walk_allocs, &W.prev_sign, 12 * n); rc |= walk_alloc(b->walk_allocs, &W.buffer_index, n); rc |= walk_alloc(b->walk_allocs, &W.sample_count, n);
+    rc |= walk_alloc(b->walk_allocs, &W.flags, n); rc |= walk_alloc(b->walk_allocs, &W.episode, n);
     if (rc) return QG_ECUDA;
     QgWalkOpts& o = b->wopts;
     o.random_controls = random_controls;
     o.auto_reset = 1;
     o.seed = b->opts.seed;
     o.env_offset = b->opts.env_offset;
-    o.min_speed = sample_opts ? sample_opts[0] : 0.0;
-    o.max_speed = sample_opts ? sample_opts[1] : 1.0;
-    o.fixed_heading = sample_opts ? sample_opts[2] : 0.0;
-    o.fixed_velocity_angle = sample_opts ? sample_opts[3] : 0.0;
-    o.fixed_speed = sample_opts ? sample_opts[4] : 0.0;
-    o.has_heading = sample_has ? sample_has[0] : 0;
-    o.has_velocity_angle = sample_has ? sample_has[1] : 0;
-    o.has_speed = sample_has ? sample_has[2] : 0;
+    qg_walk_set_sample_options(b, sample_opts, sample_has);
     for (int i = 0; i < 12; ++i) o.joint_centers[i] = b->opts.reset_ctrl[i];   // walking_quad.py:36-39 == quadruped.py:124
     b->opts.settling_time = settling_time;
     b->walk_on = true;
-    return qg_walk_reset(b, nullptr, 1, 0, 0, nullptr);
+    // hard reset with the batch's current seed / env_offset (qg_walk_reset re-keys the sampler on every call); the launch
+    // goes to the NULL stream, so wait for it: callers continue on their own (possibly non-blocking) streams
+    int rc2 = qg_walk_reset(b, nullptr, 1, b->opts.seed, b->opts.env_offset, nullptr);
+    if (rc2) return rc2;
+    CUDA_OK(cudaDeviceSynchronize());
+    return QG_OK;
 }
 
 extern "C" int qg_walk_reset(qg_batch* b, const uint8_t* mask_dev, int hard, uint64_t seed, long long env_offset, void* stream) {
     if (!b || !b->walk_on) return fail(QG_EINVAL, "qg_walk_reset: walking mode is not enabled");
     CUDA_OK(cudaSetDevice(b->device));
-    if (hard) { b->wopts.seed = seed; b->wopts.env_offset = env_offset; }
+    // the command sampler is keyed on (seed, env_offset + env, episode): always taken from the call, so that shards
+    // and seeds set after qg_walk_enable reach it (`hard` only adds: clear the estimator / first control cost / episode)
+    b->wopts.seed = seed;
+    b->wopts.env_offset = env_offset;
     qg_walk_reset_kernel<<<(b->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->walk, b->wopts, mask_dev, hard);
     g_launches++;
     CUDA_OK(cudaGetLastError());
@@ -850,7 +1017,9 @@ extern "C" int qg_po_enable(qg_batch* b, int obs_window, double Dt, double beta,
     CUDA_OK(cudaSetDevice(b->device));
     QgPoState& P = b->po;
     P.n = b->n; P.window = obs_window; P.Dt = Dt; P.beta = beta; P.settle_half = settling_time / 2;
-    if (walk_alloc(b, &P.q, 4 * (size_t)b->n) || walk_alloc(b, &P.is_view, (size_t)b->n)) return QG_ECUDA;
+    for (void* p : b->po_allocs) cudaFree(p);
+    b->po_allocs.clear();
+    if (walk_alloc(b->po_allocs, &P.q, 4 * (size_t)b->n) || walk_alloc(b->po_allocs, &P.is_view, (size_t)b->n)) return QG_ECUDA;
     std::vector<double> q0(4 * (size_t)b->n, 0.0);
     for (int i = 0; i < b->n; ++i) q0[4 * (size_t)i] = 1.0;      // computed_orientation = [1, 0, 0, 0] (po_walking_quad.py:19)
     CUDA_OK(cudaMemcpy(P.q, q0.data(), q0.size() * sizeof(double), cudaMemcpyHostToDevice));

@@ -112,6 +112,81 @@ DI void reset_lane(const QgModelC& P, LaneState& L, int leg, const QgStepOpts& o
     }
 }
 
+// state planes (HBM) -> the block's shared-memory state: every lane moves its 4 leg planes, the 8 base planes are split
+// over the quad's lanes (2 each); the caller syncs the quad before anyone reads another lane's words
+DI void planes_to_shared(const float4* __restrict__ S, int N, int env, int leg, const StateRef& R) {
+    const int pl = QG_PL_LEG0 + 4 * leg;
+    const float4 l0 = ldS(S, pl, N, env), l1 = ldS(S, pl + 1, N, env), l2 = ldS(S, pl + 2, N, env), l3 = ldS(S, pl + 3, N, env);
+    const float4 b0 = ldS(S, 2 * leg, N, env), b1 = ldS(S, 2 * leg + 1, N, env);
+    SLW(R, SL_Q) = l0.x; SLW(R, SL_Q + 1) = l0.y; SLW(R, SL_Q + 2) = l0.z; SLW(R, SL_QD) = l0.w;
+    SLW(R, SL_QD + 1) = l1.x; SLW(R, SL_QD + 2) = l1.y; SLW(R, SL_ACT) = l1.z; SLW(R, SL_ACT + 1) = l1.w;
+    SLW(R, SL_ACT + 2) = l2.x; SLW(R, SL_WJ) = l2.y; SLW(R, SL_WJ + 1) = l2.z; SLW(R, SL_WJ + 2) = l2.w;
+    SLW(R, SL_CTRL) = l3.x; SLW(R, SL_CTRL + 1) = l3.y; SLW(R, SL_CTRL + 2) = l3.z;
+    SLW(R, SL_PCTRL) = l3.x; SLW(R, SL_PCTRL + 1) = l3.y; SLW(R, SL_PCTRL + 2) = l3.z;
+    if (leg == 0) {          // QG_PL_POS, QG_PL_QUAT
+        SBW(R, SB_POS) = b0.x; SBW(R, SB_POS + 1) = b0.y; SBW(R, SB_POS + 2) = b0.z;
+        SBW(R, SB_QUAT) = b1.x; SBW(R, SB_QUAT + 1) = b1.y; SBW(R, SB_QUAT + 2) = b1.z; SBW(R, SB_QUAT + 3) = b1.w;
+    } else if (leg == 1) {   // QG_PL_VLIN, QG_PL_VANG
+        SBW(R, SB_VLIN) = b0.x; SBW(R, SB_VLIN + 1) = b0.y; SBW(R, SB_VLIN + 2) = b0.z;
+        SBW(R, SB_VANG) = b1.x; SBW(R, SB_VANG + 1) = b1.y; SBW(R, SB_VANG + 2) = b1.z;
+    } else if (leg == 2) {   // QG_PL_WLIN, QG_PL_WANG
+        SBW(R, SB_WLIN) = b0.x; SBW(R, SB_WLIN + 1) = b0.y; SBW(R, SB_WLIN + 2) = b0.z;
+        SBW(R, SB_WANG) = b1.x; SBW(R, SB_WANG + 1) = b1.y; SBW(R, SB_WANG + 2) = b1.z;
+    } else {                 // QG_PL_TIME (time lo/hi, episode), QG_PL_AUX (flags, first control cost lo/hi)
+        SBW(R, SB_TIME) = b0.x; SBW(R, SB_TIME + 1) = b0.y; SBW(R, SB_EPISODE) = b0.z;
+        SBW(R, SB_FLAGS) = b1.x; SBW(R, SB_FCC) = b1.y; SBW(R, SB_FCC + 1) = b1.z;
+    }
+}
+
+DI void shared_to_planes(float4* __restrict__ S, int N, int env, int leg, const StateRef& R) {
+    const int pl = QG_PL_LEG0 + 4 * leg;
+    stS(S, pl, N, env, make_float4(SLW(R, SL_Q), SLW(R, SL_Q + 1), SLW(R, SL_Q + 2), SLW(R, SL_QD)));
+    stS(S, pl + 1, N, env, make_float4(SLW(R, SL_QD + 1), SLW(R, SL_QD + 2), SLW(R, SL_ACT), SLW(R, SL_ACT + 1)));
+    stS(S, pl + 2, N, env, make_float4(SLW(R, SL_ACT + 2), SLW(R, SL_WJ), SLW(R, SL_WJ + 1), SLW(R, SL_WJ + 2)));
+    stS(S, pl + 3, N, env, make_float4(SLW(R, SL_CTRL), SLW(R, SL_CTRL + 1), SLW(R, SL_CTRL + 2), 0.f));
+    if (leg == 0) {
+        stS(S, QG_PL_POS, N, env, make_float4(SBW(R, SB_POS), SBW(R, SB_POS + 1), SBW(R, SB_POS + 2), 0.f));
+        stS(S, QG_PL_QUAT, N, env, make_float4(SBW(R, SB_QUAT), SBW(R, SB_QUAT + 1), SBW(R, SB_QUAT + 2), SBW(R, SB_QUAT + 3)));
+    } else if (leg == 1) {
+        stS(S, QG_PL_VLIN, N, env, make_float4(SBW(R, SB_VLIN), SBW(R, SB_VLIN + 1), SBW(R, SB_VLIN + 2), 0.f));
+        stS(S, QG_PL_VANG, N, env, make_float4(SBW(R, SB_VANG), SBW(R, SB_VANG + 1), SBW(R, SB_VANG + 2), 0.f));
+    } else if (leg == 2) {
+        stS(S, QG_PL_WLIN, N, env, make_float4(SBW(R, SB_WLIN), SBW(R, SB_WLIN + 1), SBW(R, SB_WLIN + 2), 0.f));
+        stS(S, QG_PL_WANG, N, env, make_float4(SBW(R, SB_WANG), SBW(R, SB_WANG + 1), SBW(R, SB_WANG + 2), 0.f));
+    } else {
+        stS(S, QG_PL_TIME, N, env, make_float4(SBW(R, SB_TIME), SBW(R, SB_TIME + 1), SBW(R, SB_EPISODE), 0.f));
+        stS(S, QG_PL_AUX, N, env, make_float4(SBW(R, SB_FLAGS), SBW(R, SB_FCC), SBW(R, SB_FCC + 1), 0.f));
+    }
+}
+
+// reset_lane into the shared state (lane `leg` writes its own leg words, lane 0 the base words); keep_ctrl: the
+// mid-step blow-up guard keeps data.ctrl
+DI void reset_shared(const QgModelC& P, const StateRef& R, int leg, const QgStepOpts& o, int env, int episode, bool keep_ctrl) {
+    LaneState L;
+    reset_lane(P, L, leg, o, env, episode);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        SLW(R, SL_Q + k) = L.q[k]; SLW(R, SL_QD + k) = 0.f; SLW(R, SL_ACT + k) = 0.f; SLW(R, SL_WJ + k) = 0.f;
+        if (!keep_ctrl) SLW(R, SL_CTRL + k) = L.ctrl[k];
+    }
+    if (leg == 0) {
+        SBW(R, SB_POS) = L.pb.x; SBW(R, SB_POS + 1) = L.pb.y; SBW(R, SB_POS + 2) = L.pb.z;
+        SBW(R, SB_QUAT) = L.qw; SBW(R, SB_QUAT + 1) = L.qx; SBW(R, SB_QUAT + 2) = L.qy; SBW(R, SB_QUAT + 3) = L.qz;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) SBW(R, SB_VLIN + k) = 0.f;     // vlin, vang, wlin, wang
+        sb_set_time(R, 0.0);
+    }
+}
+
+DI bool shared_bad(const StateRef& R) {
+    bool ok = true;
+#pragma unroll
+    for (int w = SB_POS; w < SB_WLIN; ++w) ok = ok && fabsf(SBW(R, w)) < 1e10f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ok = ok && fabsf(SLW(R, SL_Q + k)) < 1e10f;     // q, qd
+    return !ok;
+}
+
 DI bool lane_bad(const LaneState& L) {
     bool ok = fabsf(L.pb.x) < 1e10f && fabsf(L.pb.y) < 1e10f && fabsf(L.pb.z) < 1e10f && fabsf(L.qw) < 1e10f &&
               fabsf(L.qx) < 1e10f && fabsf(L.qy) < 1e10f && fabsf(L.qz) < 1e10f && fabsf(L.vw.x) < 1e10f &&
@@ -136,7 +211,7 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
                int clip_action, int frame_skip, float* __restrict__ obs, float* __restrict__ reward,
                float* __restrict__ terms, unsigned char* __restrict__ terminated, float* __restrict__ terminal_obs,
                QgStepOpts opts, QgCounters* __restrict__ ctr, QgDebugOut dbg, const int* __restrict__ perm,
-               unsigned char* __restrict__ bin_key, int* __restrict__ chunk_ctr, int nchunks) {
+               unsigned char* __restrict__ bin_key, int* __restrict__ chunk_ctr, int nchunks, int env0, int cnt) {
     extern __shared__ __align__(16) unsigned char smem[];
     QgModelC& P = *reinterpret_cast<QgModelC*>(smem);
     float4* sverts = reinterpret_cast<float4*>(smem + ((sizeof(QgModelC) + 15) & ~size_t(15)));
@@ -147,6 +222,9 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
     // separate the collision phase from the reductions before and after it), and 27 KB less shared memory per block is
     // 27 KB more L1 for the thread-local contact tables and link frames.
     const WarpQueue wq = warp_queue(sred);
+    // resident state of the block's environments (qg_step.cuh, StateRef), behind the reduction rows of all warps
+    float* sbase = reinterpret_cast<float*>(sverts + gm->nvert) + (blockDim.x >> 5) * (QG_QR_SLOTS * 32);
+    float* sleg = sbase + SB_NWORDS * (blockDim.x >> 2);
     {
         const int4* src = reinterpret_cast<const int4*>(gm);
         int4* dst = reinterpret_cast<int4*>(smem);
@@ -165,18 +243,22 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
     __syncthreads();   // staging done / previous chunk finished with s_chunk
     if (threadIdx.x == 0) s_chunk = atomicAdd(chunk_ctr, 1);
     __syncthreads();
-    const int chunk = s_chunk;
-    if (chunk >= nchunks) break;
+    if (s_chunk >= nchunks) break;
+    // chunks are handed out from the END of the slot order: the binning permutation sorts the environments by the solver
+    // effort of their last step, ascending, so the expensive chunks start first and the cheap ones fill the tail of the
+    // launch (longest-processing-time-first on the SMs)
+    const int chunk = nchunks - 1 - s_chunk;
     dbg = dbg_in;
     const int t = chunk * blockDim.x + threadIdx.x;
     const int leg = t & 3;
-    // quads past the end of the batch shadow the last environment (same reads, no writes) so that every thread
-    // of the block reaches the same barriers
-    const bool valid = (t >> 2) < N;
-    // `perm` (optional) maps quad slots to environments: environments with similar contact / solver effort in the
-    // previous launch share warps (less SIMT divergence); results per environment do not depend on the slot
-    const int slot = valid ? (t >> 2) : N - 1;
-    const int env = perm ? perm[slot] : slot;
+    // One launch covers the environments [env0, env0 + cnt) of the batch (the whole batch, or one segment of the
+    // pipelined host path); N stays the plane stride.  Quads past the end shadow the last environment (same reads, no
+    // writes) so that every thread of the block reaches the same barriers.
+    const bool valid = (t >> 2) < cnt;
+    // `perm` (optional, this launch's slice) maps quad slots to environments: environments with similar contact / solver
+    // effort in the previous launch share warps (less SIMT divergence); results per environment do not depend on the slot
+    const int slot = valid ? (t >> 2) : cnt - 1;
+    const int env = perm ? perm[slot] : env0 + slot;
     if (!valid) { dbg.qacc = dbg.qacc_smooth = dbg.qfrc_bias = dbg.M = dbg.sensordata = nullptr; dbg.counts = nullptr; }
     const unsigned qm = 0xFu << (threadIdx.x & 28);
     WarpCounters wc;
@@ -189,17 +271,22 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
     qr.qm = qm;
 
     {
-        LaneState L;
-        int episode, flags;
-        double first_cc;
-        load_lane(S, N, env, leg, L, episode, first_cc, flags);
-        float prev_ctrl[3] = {L.ctrl[0], L.ctrl[1], L.ctrl[2]};
+        StateRef SR;
+        SR.nb = blockDim.x >> 2;
+        SR.nl = blockDim.x;
+        SR.b = sbase + (threadIdx.x >> 2);
+        SR.l = sleg + threadIdx.x;
+        planes_to_shared(S, N, env, leg, SR);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             float a = action[(size_t)env * 12 + 3 * leg + k];
             if (clip_action) a = fminf(fmaxf(a, -1.f), 1.f);
-            if (L.time < opts.settling_time) a = opts.reset_ctrl[3 * leg + k];
-            L.ctrl[k] = a;
+            SLW(SR, SL_CTRL + k) = a;
+        }
+        __syncwarp(qm);
+        if (sb_time(SR) < opts.settling_time) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) SLW(SR, SL_CTRL + k) = opts.reset_ctrl[3 * leg + k];
         }
 
         StepStats st;
@@ -214,34 +301,39 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
 #if QG_BLOCKSYNC
             __syncthreads();
 #endif
-            if (qsumi(lane_bad(L) ? 1 : 0, qm) > 0) {  // mj_checkPos / mj_checkVel
-                float c0 = L.ctrl[0], c1 = L.ctrl[1], c2 = L.ctrl[2];
-                reset_lane(P, L, leg, opts, env, episode);
-                L.ctrl[0] = c0; L.ctrl[1] = c1; L.ctrl[2] = c2;
+            if (qsumi(shared_bad(SR) ? 1 : 0, qm) > 0) {  // mj_checkPos / mj_checkVel
+                __syncwarp(qm);
+                reset_shared(P, SR, leg, opts, env, __float_as_int(SBW(SR, SB_EPISODE)), true);
+                __syncwarp(qm);
                 diverged += (leg == 0);
             }
-            physics_step<DEBUG, CONE>(P, sverts, adj4, cadj4, L, leg, qr, wq, max_iter, ls_iter, s == frame_skip - 1, so,
+            physics_step<DEBUG, CONE>(P, sverts, adj4, cadj4, SR, leg, qr, wq, max_iter, ls_iter, s == frame_skip - 1, so,
                                 st, wc, C, dbg, env);
         }
+        // the epilogue's view of the state after the step
+        int episode = __float_as_int(SBW(SR, SB_EPISODE)), flags = __float_as_int(SBW(SR, SB_FLAGS));
+        double first_cc = __hiloint2double(__float_as_int(SBW(SR, SB_FCC + 1)), __float_as_int(SBW(SR, SB_FCC)));
+        const double time_now = sb_time(SR);
+        const float vw_x = SBW(SR, SB_VLIN);
 
         // ---- reward terms (float64 from the float32 sensordata / ctrl / state, reference formulas)
         double total = 0.0;
         if (opts.n_terms > 0) {
-            const int lane0 = (threadIdx.x & 31) & ~3;
+            const float* q0 = sleg + (threadIdx.x & ~3);     // leg words of the quad's lane 0
             double call[12], pall[12];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    call[3 * j + k] = (double)__shfl_sync(qm, L.ctrl[k], lane0 + j);
-                    pall[3 * j + k] = (double)__shfl_sync(qm, prev_ctrl[k], lane0 + j);
+                    call[3 * j + k] = (double)q0[(SL_CTRL + k) * SR.nl + j];
+                    pall[3 * j + k] = (double)q0[(SL_PCTRL + k) * SR.nl + j];
                 }
             for (int i = 0; i < opts.n_terms; ++i) {
                 double v = 0.0, p = opts.term_p[i];
                 switch (opts.term_id[i]) {
                     case 0: v = 1.0; break;
                     case 1: { double sq[12]; for (int k = 0; k < 12; ++k) sq[k] = call[k] * call[k]; v = np_sum12(sq); } break;
-                    case 2: v = (double)L.vw.x; break;
+                    case 2: v = (double)vw_x; break;
                     case 3: v = (double)so.linvel.x * (double)so.pos.x; break;
                     case 4: v = fabs((double)so.linvel.y * (double)so.pos.y); break;
                     case 5: {
@@ -269,7 +361,7 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
         }
 
         // ---- termination (time limit is `terminated`, never truncated: quadruped.py:149-151,178-179)
-        const bool term = (L.time >= opts.max_time) || (opts.flip_termination && so.zaxis.z < 0.f);
+        const bool term = (time_now >= opts.max_time) || (opts.flip_termination && so.zaxis.z < 0.f);
         if (leg == 0 && valid) {
             reward[env] = (float)total;
             terminated[env] = term ? 1 : 0;
@@ -308,11 +400,16 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
             }
         }
         }
-        if (do_reset) {
-            episode++;
-            reset_lane(P, L, leg, opts, env, episode);
+        __syncwarp(qm);          // all four lanes are done reading the shared state
+        if (leg == 3) {          // episode counter and reward memory back to the shared words the store below reads
+            SBW(SR, SB_FLAGS) = __int_as_float(flags);
+            SBW(SR, SB_FCC) = __int_as_float(__double2loint(first_cc));
+            SBW(SR, SB_FCC + 1) = __int_as_float(__double2hiint(first_cc));
+            SBW(SR, SB_EPISODE) = __int_as_float(do_reset ? episode + 1 : episode);
         }
-        if (valid) store_lane(S, N, env, leg, L, episode, first_cc, flags);
+        if (do_reset) reset_shared(P, SR, leg, opts, env, episode + 1, false);
+        __syncwarp(qm);
+        if (valid) shared_to_planes(S, N, env, leg, SR);
 
         wc_add(wc, QG_C_STEPS, leg == 0 ? frame_skip : 0);
         wc_add(wc, QG_C_DIVERGED, diverged);
@@ -453,7 +550,7 @@ __global__ void qg_bin_hist_kernel(const unsigned char* __restrict__ key, int N,
     if (threadIdx.x < QG_NBINS && sc[threadIdx.x]) atomicAdd(&count[threadIdx.x], sc[threadIdx.x]);
 }
 __global__ void qg_bin_scatter_kernel(const unsigned char* __restrict__ key, int N, const int* __restrict__ count,
-                                      int* __restrict__ cursor, int* __restrict__ perm) {
+                                      int* __restrict__ cursor, int* __restrict__ perm, int env0) {
     __shared__ int base[QG_NBINS], sc[QG_NBINS], sbase[QG_NBINS];
     if (threadIdx.x == 0) {
         int acc = 0;
@@ -467,5 +564,5 @@ __global__ void qg_bin_scatter_kernel(const unsigned char* __restrict__ key, int
     __syncthreads();
     if (threadIdx.x < QG_NBINS && sc[threadIdx.x]) sbase[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], sc[threadIdx.x]);
     __syncthreads();
-    if (e < N) perm[base[b] + sbase[b] + local] = e;
+    if (e < N) perm[base[b] + sbase[b] + local] = env0 + e;   // key / perm point at the slice, ids are absolute
 }

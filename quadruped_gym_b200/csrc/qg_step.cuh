@@ -34,6 +34,38 @@ struct LaneState {
     float q[3], qd[3], act[3], wj[3], ctrl[3];
 };
 
+// The state of the environments a block is stepping lives in SHARED MEMORY for the whole env.step(), de-replicated: the
+// base words once per environment, the leg words once per lane.  physics_step reads what a stage needs when it needs it
+// (nothing of the state is carried in registers across the solver), and writes the integrated state back at the end.
+// Word w of environment slot e: base[w * nb + e]; word w of lane t: leg[w * nl + t]  (a warp's 8 environments read 8
+// consecutive words with a 4-lane broadcast each; leg words are consecutive over the lanes: no bank conflicts).
+enum { SB_POS = 0, SB_QUAT = 3, SB_VLIN = 7, SB_VANG = 10, SB_WLIN = 13, SB_WANG = 16, SB_TIME = 19 /* lo, hi */,
+       SB_EPISODE = 21, SB_FLAGS = 22, SB_FCC = 23 /* first control cost: lo, hi */, SB_NWORDS = 25 };
+enum { SL_Q = 0, SL_QD = 3, SL_ACT = 6, SL_WJ = 9, SL_CTRL = 12, SL_PCTRL = 15 /* data.ctrl before this env.step() */, SL_NWORDS = 18 };
+struct StateRef {
+    float* b;   // this environment's base word 0
+    float* l;   // this lane's leg word 0
+    int nb, nl; // strides between words (environments / threads per block)
+};
+DI float& SBW(const StateRef& r, int w) { return r.b[w * r.nb]; }
+DI float& SLW(const StateRef& r, int w) { return r.l[w * r.nl]; }
+DI v3 sb3(const StateRef& r, int w) { return V3(SBW(r, w), SBW(r, w + 1), SBW(r, w + 2)); }
+DI double sb_time(const StateRef& r) { return __hiloint2double(__float_as_int(SBW(r, SB_TIME + 1)), __float_as_int(SBW(r, SB_TIME))); }
+DI void sb_set_time(const StateRef& r, double t) {
+    SBW(r, SB_TIME) = __int_as_float(__double2loint(t));
+    SBW(r, SB_TIME + 1) = __int_as_float(__double2hiint(t));
+}
+// pose and velocities of the base and the lane's joint state (what the forward pass reads); the warm start is read where
+// the solver needs it
+DI void state_load(const StateRef& r, LaneState& S) {
+    S.pb = sb3(r, SB_POS);
+    S.qw = SBW(r, SB_QUAT); S.qx = SBW(r, SB_QUAT + 1); S.qy = SBW(r, SB_QUAT + 2); S.qz = SBW(r, SB_QUAT + 3);
+    S.vw = sb3(r, SB_VLIN);
+    S.om = sb3(r, SB_VANG);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { S.q[k] = SLW(r, SL_Q + k); S.qd[k] = SLW(r, SL_QD + k); S.act[k] = SLW(r, SL_ACT + k); S.ctrl[k] = SLW(r, SL_CTRL + k); }
+}
+
 struct SensorOut {
     float jq[3];
     v3 acc, gyro, pos, linvel, xaxis, zaxis, vel;
@@ -487,12 +519,14 @@ DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const 
 // ---------------------------------------------------------------------------------------------
 template <bool DEBUG, int CONE>
 DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const int4* __restrict__ adj4,
-                     const int4* __restrict__ cadj4, LaneState& S, int leg, const QuadRed& qr, const WarpQueue& wq,
+                     const int4* __restrict__ cadj4, const StateRef& SR, int leg, const QuadRed& qr, const WarpQueue& wq,
                      int max_iter, int ls_iter, bool want_sensors, SensorOut& so, StepStats& st, const WarpCounters& wc, Contacts& C,
                      const QgDebugOut& dbg, int env) {
     const float h = P.timestep;
     constexpr int NR = CONE ? 3 : 4;   // rows per contact
     const float mus = P.mu_scale, impr = P.impratio;
+    LaneState S;          // forward-pass copy of the state: its members die with their last use before the solver
+    state_load(SR, S);
     // ---- base frame
     float qn = 1.f / sqrtf(S.qw * S.qw + S.qx * S.qx + S.qy * S.qy + S.qz * S.qz);
     float w = S.qw * qn, x = S.qx * qn, y = S.qy * qn, z = S.qz * qn;
@@ -768,11 +802,12 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
             if (nefc == 0) conv = true;
             else {
                 // warm start: compare the cost at qacc_warmstart and at qacc_smooth (mj_fwdConstraint)
-                v3 wlB = tmul(Rb, S.wl);
-                float wb[6] = {wlB.x, wlB.y, wlB.z, S.wa.x, S.wa.y, S.wa.z};
+                v3 wlB = tmul(Rb, sb3(SR, SB_WLIN));
+                float wb[6] = {wlB.x, wlB.y, wlB.z, SBW(SR, SB_WANG), SBW(SR, SB_WANG + 1), SBW(SR, SB_WANG + 2)};
+                float wj[3] = {SLW(SR, SL_WJ), SLW(SR, SL_WJ + 1), SLW(SR, SL_WJ + 2)};
                 float cw = 0.f, cs = 0.f;
                 v3 U2[4], W2[4];
-                twist(wb, S.wj, sl, sa, U, W);
+                twist(wb, wj, sl, sa, U, W);
                 twist(a0b, a0l, sl, sa, U2, W2);
 #pragma unroll 1
                 for (int c = 0; c < nc; ++c) {
@@ -806,17 +841,17 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
                     float4 r = lim[s];
                     const int k = (int)fabsf(r.x) - 1;
                     const float sg = r.x < 0.f ? -1.f : 1.f;
-                    float jw = fmaf(sg, sel3(S.wj, k), r.z), js = fmaf(sg, sel3(a0l, k), r.z);
+                    float jw = fmaf(sg, sel3(wj, k), r.z), js = fmaf(sg, sel3(a0l, k), r.z);
                     cw += (jw < 0.f) ? 0.5f * r.y * jw * jw : 0.f;
                     cs += (js < 0.f) ? 0.5f * r.y * js * js : 0.f;
                     lim[s] = make_float4(r.x, r.y, jw, js);   // .w parks the value at qacc_smooth
                 }
                 // M w: lane-local part now, base rows from the same reduction that sums the two costs
                 float Mwb[6], Mwl[3], Mwp[6];
-                arrow_matvec_local(Mll, Mbl, wb, S.wj, Mwp, Mwl);
+                arrow_matvec_local(Mll, Mbl, wb, wj, Mwp, Mwl);
                 float gl = 0.f, gb = 0.f;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) gl += 0.5f * (Mwl[k] - fsl[k]) * (S.wj[k] - a0l[k]);
+                for (int k = 0; k < 3; ++k) gl += 0.5f * (Mwl[k] - fsl[k]) * (wj[k] - a0l[k]);
                 qr_put(qr, 0, cw + gl); qr_put(qr, 1, cs);
 #pragma unroll
                 for (int r = 0; r < 6; ++r) qr_put(qr, 2 + r, Mwp[r]);
@@ -835,7 +870,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
 #pragma unroll
                     for (int i = 0; i < 6; ++i) { ab[i] = wb[i]; Mab[i] = Mwb[i]; }
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) { al[i] = S.wj[i]; Mal[i] = Mwl[i]; }
+                    for (int i = 0; i < 3; ++i) { al[i] = wj[i]; Mal[i] = Mwl[i]; }
                 } else {
 #pragma unroll 1
                     for (int c = 0; c < nc; ++c) C.jar[c] = C.jv[c];
@@ -1165,16 +1200,20 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
     if (DEBUG) { st.niter += (leg == 0) ? iter : 0; st.nls += nls; }
     st.last_ls = nls;
 
+    // ---- the state again, from shared memory (nothing of it was held across the solver)
+    LaneState E;
+    state_load(SR, E);
+    const v3 vB2 = tmul(Rb, E.vw);
     // ---- sensors of this forward pass (pre-integration state, solver qacc)
     if (want_sensors) {
-        so.jq[0] = S.q[0]; so.jq[1] = S.q[1]; so.jq[2] = S.q[2];
-        so.acc = V3(ab[0], ab[1], ab[2]) - gB;
-        so.gyro = S.om;
-        so.pos = S.pb;
-        so.linvel = S.vw;
+        so.jq[0] = E.q[0]; so.jq[1] = E.q[1]; so.jq[2] = E.q[2];
+        so.acc = V3(ab[0], ab[1], ab[2]) - tmul(Rb, ld3(P.grav));
+        so.gyro = E.om;
+        so.pos = E.pb;
+        so.linvel = E.vw;
         so.xaxis = col0(Rb);
         so.zaxis = col2(Rb);
-        so.vel = vB;
+        so.vel = vB2;
     }
     if (DEBUG) {
         v3 aw = mul(Rb, V3(ab[0], ab[1], ab[2])), a0w = mul(Rb, V3(a0b[0], a0b[1], a0b[2]));
@@ -1218,36 +1257,49 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
     }
 
     // ---- semi-implicit update with qacc+ = (xb, xl); warm start for the next step = solver acceleration
-    S.wl = mul(Rb, V3(ab[0], ab[1], ab[2]));
-    S.wa = V3(ab[3], ab[4], ab[5]);
+    const v3 wl = mul(Rb, V3(ab[0], ab[1], ab[2]));
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        S.wj[k] = al[k];
+        SLW(SR, SL_WJ + k) = al[k];
         {   // activation dynamics: act_dot = (clamp(ctrl) - act) / tau, exact first-order filter over h
             const QgJointC& J = P.joint[leg][k];
             if (J.has_act && J.has_dyn) {
-                float c = S.ctrl[k];
+                float c = E.ctrl[k];
                 if (J.ctrl_limited) c = fminf(fmaxf(c, J.ctrl_lo), J.ctrl_hi);
-                S.act[k] = fmaf((c - S.act[k]) * J.inv_tau, J.act_fac, S.act[k]);
+                SLW(SR, SL_ACT + k) = fmaf((c - E.act[k]) * J.inv_tau, J.act_fac, E.act[k]);
             }
         }
-        S.qd[k] = fmaf(h, xl[k], S.qd[k]);
-        S.q[k] = fmaf(h, S.qd[k], S.q[k]);
+        const float qd = fmaf(h, xl[k], E.qd[k]);
+        SLW(SR, SL_QD + k) = qd;
+        SLW(SR, SL_Q + k) = fmaf(h, qd, E.q[k]);
     }
-    v3 vBn = fma3(h, V3(xb[0], xb[1], xb[2]), vB);
-    S.vw = mul(Rb, vBn);
-    S.om = fma3(h, V3(xb[3], xb[4], xb[5]), S.om);
-    S.pb = fma3(h, S.vw, S.pb);
-    float wn = sqrtf(dot(S.om, S.om));
+    const v3 vBn = fma3(h, V3(xb[0], xb[1], xb[2]), vB2);
+    const v3 vwn = mul(Rb, vBn);
+    const v3 omn = fma3(h, V3(xb[3], xb[4], xb[5]), E.om);
+    const v3 pbn = fma3(h, vwn, E.pb);
+    float wn = sqrtf(dot(omn, omn));
     float rw = 1.f, rx = 0.f, ry = 0.f, rz = 0.f;
     if (wn > 1e-15f) {
         float2 sc = sincos_ni(0.5f * h * wn);
         float s = sc.x / wn;
-        rw = sc.y; rx = S.om.x * s; ry = S.om.y * s; rz = S.om.z * s;
+        rw = sc.y; rx = omn.x * s; ry = omn.y * s; rz = omn.z * s;
     }
-    S.qw = w * rw - x * rx - y * ry - z * rz;
-    S.qx = w * rx + x * rw + y * rz - z * ry;
-    S.qy = w * ry - x * rz + y * rw + z * rx;
-    S.qz = w * rz + x * ry - y * rx + z * rw;
-    S.time += P.timestep_d;
+    // the normalised quaternion of this step's forward pass, recomputed from the stored one (same arithmetic, same bits)
+    const float qn2 = 1.f / sqrtf(E.qw * E.qw + E.qx * E.qx + E.qy * E.qy + E.qz * E.qz);
+    const float w2 = E.qw * qn2, x2 = E.qx * qn2, y2 = E.qy * qn2, z2 = E.qz * qn2;
+    const double tnew = sb_time(SR) + P.timestep_d;
+    __syncwarp(qr.qm);           // every lane of the quad has read the old base state
+    if (leg == 0) {              // the four lanes hold identical values: one of them writes the base words
+        SBW(SR, SB_POS) = pbn.x; SBW(SR, SB_POS + 1) = pbn.y; SBW(SR, SB_POS + 2) = pbn.z;
+        SBW(SR, SB_QUAT) = w2 * rw - x2 * rx - y2 * ry - z2 * rz;
+        SBW(SR, SB_QUAT + 1) = w2 * rx + x2 * rw + y2 * rz - z2 * ry;
+        SBW(SR, SB_QUAT + 2) = w2 * ry - x2 * rz + y2 * rw + z2 * rx;
+        SBW(SR, SB_QUAT + 3) = w2 * rz + x2 * ry - y2 * rx + z2 * rw;
+        SBW(SR, SB_VLIN) = vwn.x; SBW(SR, SB_VLIN + 1) = vwn.y; SBW(SR, SB_VLIN + 2) = vwn.z;
+        SBW(SR, SB_VANG) = omn.x; SBW(SR, SB_VANG + 1) = omn.y; SBW(SR, SB_VANG + 2) = omn.z;
+        SBW(SR, SB_WLIN) = wl.x; SBW(SR, SB_WLIN + 1) = wl.y; SBW(SR, SB_WLIN + 2) = wl.z;
+        SBW(SR, SB_WANG) = ab[3]; SBW(SR, SB_WANG + 1) = ab[4]; SBW(SR, SB_WANG + 2) = ab[5];
+        sb_set_time(SR, tnew);
+    }
+    __syncwarp(qr.qm);
 }

@@ -8,7 +8,7 @@ installable here): restated from its published algorithm, parity unpinned (SURVE
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import Optional
 
 import numpy as np
 import torch
@@ -36,7 +36,7 @@ class VecPOWalkingQuadrupedEnv(VecWalkingQuadrupedEnv):
         # runs inside walking_quad.py:103): fill the stack first, then do the walking / physics reset
         super(VecWalkingQuadrupedEnv, self).reset(seed=seed, options=options, mask=mask)
         _lib.check(_lib.lib().qg_po_observe(self._batch, None, _ptr(m), _ptr(self._stacked), None, 1, 1, self._stream()), "qg_po_observe")
-        _lib.check(_lib.lib().qg_walk_reset(self._batch, _ptr(m), 0, self.seed_value, self.env_offset, self._stream()), "qg_walk_reset")
+        self._walk_reset(m, options)
         self.info = {}
         return self._stacked, self.info
 
@@ -64,75 +64,8 @@ class VecPOWalkingQuadrupedEnv(VecWalkingQuadrupedEnv):
         return self._stacked, self._reward, terminated, self._truncated, self.info
 
 
-class SB3VecEnvAdapter:
-    """stable-baselines3 ``VecEnv`` surface over a vectorised env of this package: numpy in / numpy out, one D2H
-    copy per step, same-step auto-reset with ``infos[i]["terminal_observation"]`` and ``"TimeLimit.truncated"``,
-    and the 11 reward keys in every info dict (RewardCallback._on_step indexes them unconditionally,
-    /root/reference/src/train_quadruped.py:86-92).  Duck-typed: SB3 itself is not required (nor installed here)."""
-
-    def __init__(self, env):
-        if not env.auto_reset:
-            raise ValueError("SB3 VecEnv semantics need auto_reset=True")
-        self.env = env
-        self.num_envs = env.num_envs
-        self.observation_space, self.action_space = env.observation_space, env.action_space
-        self.render_mode = None
-        self._actions = None
-        self.reward_keys = list(getattr(env, "reward_keys", []))
-
-    def reset(self):
-        obs, _ = self.env.reset()
-        return obs.cpu().numpy()
-
-    def step_async(self, actions):
-        self._actions = np.asarray(actions, dtype=np.float32)
-
-    def step_wait(self):
-        obs, rew, term, trunc, info = self.env.step(torch.from_numpy(self._actions))
-        # one packed D2H transfer: obs | reward | done | per-term rewards
-        keys = self.reward_keys
-        terms = torch.stack([info[k] for k in keys], dim=1) if keys else torch.zeros((self.num_envs, 0), device=obs.device)
-        packed = torch.cat([obs, rew[:, None], term[:, None].float(), terms], dim=1).cpu().numpy()
-        d = obs.shape[1]
-        o, r, done, tv = packed[:, :d], packed[:, d], packed[:, d + 1] > 0.5, packed[:, d + 2:]
-        tobs = info["terminal_observation"][term].cpu().numpy() if done.any() else None
-        infos: List[dict] = []
-        j = 0
-        for i in range(self.num_envs):
-            di = {k: float(tv[i, c]) for c, k in enumerate(keys)}
-            di["TimeLimit.truncated"] = False        # the reference reports the time limit as terminated
-            if done[i]:
-                di["terminal_observation"] = tobs[j]
-                j += 1
-            infos.append(di)
-        return o.copy(), r.copy(), done, infos
-
-    def step(self, actions):
-        self.step_async(actions)
-        return self.step_wait()
-
-    def close(self):
-        self.env.close()
-
-    def seed(self, seed=None):
-        return [self.env.seed(seed)] * self.num_envs
-
-    def get_attr(self, name, indices=None):
-        n = self.num_envs if indices is None else len(list(indices))
-        return [getattr(self.env, name)] * n
-
-    def set_attr(self, name, value, indices=None):
-        setattr(self.env, name, value)
-
-    def env_method(self, method_name, *args, indices=None, **kwargs):
-        return [getattr(self.env, method_name)(*args, **kwargs)]
-
-    def env_is_wrapped(self, wrapper_class, indices=None):
-        n = self.num_envs if indices is None else len(list(indices))
-        return [False] * n
-
-    def get_images(self):
-        return [None] * self.num_envs
-
-    def render(self, mode=None):
-        return None
+def __getattr__(name):   # the SB3 adapter moved to envs/sb3.py; the old import path keeps working
+    if name in ("SB3VecEnvAdapter", "SB3VecEnv"):
+        from . import sb3
+        return getattr(sb3, name)
+    raise AttributeError(name)

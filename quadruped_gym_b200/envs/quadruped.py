@@ -6,8 +6,9 @@ Mirrors the interface of the reference's base environment
 surface that reward callables touch (walking_quad.py:19-20,56,93,142,253,393).  All N environments
 live in device memory owned by libquadgym; one ``step`` is ONE kernel launch.
 
-Rendering (quadruped.py:184-316) is out of scope except for a thin bridge: ``render_mode="rgb_array"`` copies one
-environment's qpos to a CPU ``mujoco.MjData`` and uses MuJoCo's renderer (only where the ``mujoco`` wheel is installed).
+Rendering (quadruped.py:184-316) is a bridge (``render.py``): ``render()`` copies one environment's qpos to a CPU
+``mujoco.MjData`` and uses MuJoCo's renderer with the reference's pacing ("human" window, "rgb_array", video); it needs
+the ``mujoco`` wheel and fails loudly at the first ``render()`` call without it.
 """
 from __future__ import annotations
 
@@ -129,10 +130,11 @@ class VecQuadrupedEnv:
                  termination_fns: Optional[dict] = None, use_default_termination: bool = True,
                  auto_reset: bool = True, seed: int = 0, env_offset: int = 0, random_init: bool = False,
                  mesh_inertia: str = "legacy", model_blob: Optional[bytes] = None, **unused_render_kwargs):
-        if render_mode not in (None, "rgb_array"):
-            raise NotImplementedError("only render_mode=None or 'rgb_array' (MuJoCo bridge, needs the mujoco wheel) is supported")
+        if render_mode not in (None, "human", "rgb_array"):
+            raise ValueError(f"unknown render_mode {render_mode!r} (quadruped.py:39: human, rgb_array)")
         self.render_mode = render_mode
         self._renderer = None
+        self._render_kwargs = {k: unused_render_kwargs[k] for k in ("width", "height", "render_fps", "save_video", "video_path") if k in unused_render_kwargs}
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.QuadGymLibraryError("VecQuadrupedEnv needs a CUDA device; there is no CPU fallback")
@@ -157,6 +159,7 @@ class VecQuadrupedEnv:
         self._terminated = torch.zeros((n,), dtype=torch.uint8, device=dev)
         self._terms = torch.zeros((n, _lib.QG_MAX_TERMS), dtype=torch.float32, device=dev)
         self._truncated = torch.zeros((n,), dtype=torch.bool, device=dev)   # quadruped.py:179: never truncated
+        self._zero_reward = torch.zeros((n,), dtype=torch.float32, device=dev)
         # env.data.sensordata is materialised on demand (no per-step kernel for a field few callers read)
         self._sd = torch.zeros((n, 33), dtype=torch.float32, device=dev)
         self._sd_pending, self._sd_merge = False, False
@@ -174,16 +177,18 @@ class VecQuadrupedEnv:
 
     def _default_reward(self):
         """Default reward function that returns 0 (quadruped.py:145-147)."""
-        return torch.zeros((self.num_envs,), dtype=torch.float32, device=self.device)
+        return self._zero_reward
 
     def _sync_tables(self):
         """Push the fused parts of reward_fns / termination_fns to the library when the dicts change."""
         fused = [(k, v) for k, v in self.reward_fns.items() if isinstance(v, R.FusedTerm)]
-        pyfn = [(k, v) for k, v in self.reward_fns.items() if not isinstance(v, R.FusedTerm)]
+        # the built-in default reward (constant 0, quadruped.py:145-147) needs no evaluation and does not block the in-kernel reset
+        zero = [k for k, v in self.reward_fns.items() if v == self._default_reward]
+        pyfn = [(k, v) for k, v in self.reward_fns.items() if not isinstance(v, R.FusedTerm) and k not in zero]
         kinds = [v.kind for v in self.termination_fns.values() if isinstance(v, R.FusedTermination)]
         pyterm = [(k, v) for k, v in self.termination_fns.items() if not isinstance(v, R.FusedTermination)]
-        key = (tuple((k, v) for k, v in fused), tuple(kinds), len(pyterm), self.max_time, self.auto_reset)
-        self._fused, self._pyfn, self._pyterm = fused, pyfn, pyterm
+        key = (tuple((k, v) for k, v in fused), tuple(kinds), len(pyterm), len(pyfn), self.max_time, self.auto_reset)
+        self._fused, self._pyfn, self._pyterm, self._zero_terms = fused, pyfn, pyterm, zero
         if key == self._table_key:
             return
         L = _lib.lib()
@@ -193,7 +198,9 @@ class VecQuadrupedEnv:
         p = (C.c_double * max(n, 1))(*[float(v.param) for _, v in fused])
         _lib.check(L.qg_set_reward_table(self._batch, n, ids, w, p), "qg_set_reward_table")
         max_time = self.max_time if "time_limit" in kinds else float("inf")
-        kernel_reset = self.auto_reset and not pyterm  # python terminations are OR-ed after the launch
+        # Python callables (rewards and terminations) are evaluated after the launch on the terminal state, exactly
+        # where the reference evaluates them (quadruped.py:170-178): the reset then happens after them, not in the kernel
+        kernel_reset = self.auto_reset and not pyterm and not pyfn
         _lib.check(L.qg_set_options(self._batch, max_time, int("flip" in kinds), int(kernel_reset), 0, 0), "qg_set_options")
         self._kernel_reset = kernel_reset
         self._table_key = key
@@ -247,17 +254,18 @@ class VecQuadrupedEnv:
             tv = self._terms[:, :nterm] if nterm == _lib.QG_MAX_TERMS else self._terms.view(-1)[: self.num_envs * nterm].view(self.num_envs, nterm)
             for i, (k, _) in enumerate(self._fused):
                 info["reward_components"][k] = tv[:, i]
+        for k in self._zero_terms:
+            info["reward_components"][k] = self._zero_reward
         for k, fn in self._pyfn:
             r = fn()
             r = torch.as_tensor(r, device=self.device, dtype=torch.float32).expand(self.num_envs)
             info["reward_components"][k] = r
             reward = reward + r
-        if self._pyterm:
-            for _, fn in self._pyterm:
-                terminated = terminated | torch.as_tensor(fn(), device=self.device).bool().expand(self.num_envs)
-            if self.auto_reset and bool(terminated.any()):
-                self._term_obs = torch.where(terminated[:, None], self._obs, torch.zeros_like(self._obs))
-                self.reset(mask=terminated)
+        for _, fn in self._pyterm:
+            terminated = terminated | torch.as_tensor(fn(), device=self.device).bool().expand(self.num_envs)
+        if self.auto_reset and not self._kernel_reset and bool(terminated.any()):
+            self._term_obs = torch.where(terminated[:, None], self._obs, torch.zeros_like(self._obs))
+            self.reset(mask=terminated)
         info["terminal_observation"] = self._term_obs
         return self._obs, reward, terminated, self._truncated, info
 
@@ -268,44 +276,55 @@ class VecQuadrupedEnv:
             self._h_act = self._h_act_t.numpy()
         return self._h_act
 
-    def step_host(self, action: np.ndarray):
-        """End-to-end call with HOST buffers (numpy in, numpy out): qg_step_host.  The returned arrays are views of
-        page-locked buffers owned by the env (valid until the next call)."""
+    def step_host(self, action: np.ndarray, want_terms: bool = False, want_terminal_obs: bool = False, wait: bool = True):
+        """End-to-end call with HOST buffers (numpy in, numpy out): qg_step_host -- segments of the batch are pipelined
+        so that the PCIe copies run under the kernels.  The returned arrays are views of page-locked buffers owned by
+        the env (valid until the next call).  ``wait=False`` returns right after enqueueing (``host_wait()`` completes
+        the step); info carries the fused reward terms / terminal observations when asked for."""
         self._sync_tables()
         a = np.ascontiguousarray(action, dtype=np.float32).reshape(self.num_envs, 12)
+        n = self.num_envs
         if not hasattr(self, "_h_obs"):
-            self._h_out = [torch.empty((self.num_envs, 33), dtype=torch.float32).pin_memory(),
-                           torch.empty((self.num_envs,), dtype=torch.float32).pin_memory(),
-                           torch.empty((self.num_envs,), dtype=torch.uint8).pin_memory()]
+            self._h_out = [torch.empty((n, 33), dtype=torch.float32).pin_memory(), torch.empty((n,), dtype=torch.float32).pin_memory(),
+                           torch.empty((n,), dtype=torch.uint8).pin_memory()]
             self._h_obs, self._h_rew, self._h_term = (t.numpy() for t in self._h_out)
-        _lib.check(_lib.lib().qg_step_host(self._batch, a.ctypes.data_as(C.c_void_p), self.frame_skip,
-                                           self._h_obs.ctypes.data_as(C.c_void_p), self._h_rew.ctypes.data_as(C.c_void_p),
-                                           self._h_term.ctypes.data_as(C.c_void_p), self._stream()), "qg_step_host")
-        return self._h_obs, self._h_rew, self._h_term.astype(bool), np.zeros(self.num_envs, dtype=bool), {}
+            self._h_terms_t = self._h_tobs_t = None
+        nterm = len(self._fused)
+        if want_terms and nterm and self._h_terms_t is None:
+            self._h_terms_t = torch.empty((n * _lib.QG_MAX_TERMS,), dtype=torch.float32).pin_memory()
+        if want_terminal_obs and self._h_tobs_t is None:
+            self._h_tobs_t = torch.zeros((n, 33), dtype=torch.float32).pin_memory()
+        vp = lambda x: x.ctypes.data_as(C.c_void_p)
+        terms = self._h_terms_t.numpy() if (want_terms and nterm) else None
+        tobs = self._h_tobs_t.numpy() if want_terminal_obs else None
+        fn = _lib.lib().qg_step_host if wait else _lib.lib().qg_step_host_async
+        _lib.check(fn(self._batch, vp(a), self.frame_skip, vp(self._h_obs), vp(self._h_rew), None if terms is None else vp(terms),
+                      vp(self._h_term), None if tobs is None else vp(tobs), self._stream()), "qg_step_host")
+        self._sd_pending, self._sd_merge = False, False
+        info = {}
+        if terms is not None:
+            tv = terms[: n * nterm].reshape(n, nterm)
+            info["reward_components"] = {k: tv[:, i] for i, (k, _) in enumerate(self._fused)}
+        if tobs is not None:
+            info["terminal_observation"] = tobs
+        return self._h_obs, self._h_rew, self._h_term.view(np.bool_), np.zeros(n, dtype=bool), info
 
-    def render(self, index: int = 0, width: int = 720, height: int = 480):
-        """Rendering bridge: copy ONE environment's qpos to a CPU ``mujoco.MjData`` and render it with
-        MuJoCo's own renderer, camera as in the reference (quadruped.py:77-86,250-306).  Needs the ``mujoco`` wheel and
-        an MJCF ``model_path``; the batched physics never depends on it."""
-        if self.render_mode != "rgb_array":
+    def host_wait(self):
+        """Block until the outputs of the last ``step_host(wait=False)`` are in the host buffers."""
+        _lib.check(_lib.lib().qg_host_wait(self._batch, self._stream()), "qg_host_wait")
+
+    def render(self, index: int = 0, overlays=()):
+        """Rendering bridge: draw ONE environment through a CPU ``mujoco`` renderer with the reference's
+        camera, pacing and modes (quadruped.py:77-86,250-306).  Needs the ``mujoco`` wheel; the batched physics never
+        depends on it."""
+        if self.render_mode is None and not self._render_kwargs.get("save_video"):
             return None
-        try:
-            import mujoco
-        except ImportError as e:  # pragma: no cover - mujoco is not installable in the build container
-            raise NotImplementedError("render() needs the `mujoco` wheel (CPU renderer bridge)") from e
-        if self._renderer is None:  # pragma: no cover
-            if not (self.model_path and str(self.model_path).endswith(".xml")):
-                raise ValueError("render() needs the env to be built from an MJCF model_path")
-            m = mujoco.MjModel.from_xml_path(self.model_path)
-            cam = mujoco.MjvCamera()
-            cam.distance, cam.elevation, cam.azimuth = 1.0, -30, 120
-            self._renderer = (m, mujoco.MjData(m), mujoco.Renderer(m, width=width, height=height), cam)
-        m, d, r, cam = self._renderer  # pragma: no cover
-        d.qpos[:] = self.data.qpos[index].double().cpu().numpy()
-        mujoco.mj_forward(m, d)
-        cam.lookat[:] = d.qpos[:3]
-        r.update_scene(d, camera=cam)
-        return r.render()
+        if self._renderer is None:
+            from .render import MujocoRenderBridge
+            kw = self._render_kwargs
+            self._renderer = MujocoRenderBridge(self.model_path, self.render_mode, kw.get("width", 720), kw.get("height", 480),
+                                                kw.get("render_fps", 30), kw.get("save_video", False), kw.get("video_path", "videos/simulation.mp4"))
+        return self._renderer.frame(self.data.qpos[index].double().cpu().numpy(), float(self.data.time[index]), overlays)
 
     # -- state access for parity tests -----------------------------------------------------------
     def set_state(self, qpos=None, qvel=None, act=None, qacc_warmstart=None, time=None, ctrl=None):
@@ -338,6 +357,9 @@ class VecQuadrupedEnv:
 
     def close(self):
         L = _lib.lib()
+        if getattr(self, "_renderer", None) is not None:
+            self._renderer.close()
+            self._renderer = None
         if getattr(self, "_batch", None):
             L.qg_batch_destroy(self._batch)
             self._batch = None
@@ -358,7 +380,7 @@ class QuadrupedEnv(_EnvBase):
     Reward / termination callables are zero-argument Python functions over ``env.data`` / ``env.model``
     as in the reference; fused specs from ``rewards`` are accepted too."""
 
-    metadata = {"render_modes": ["rgb_array"], "render_fps": 30}
+    metadata = {"render_modes": ["human", "rgb_array"], "render_fps": 30}
 
     def __init__(self, model_path: Optional[str] = None, max_time: float = 10.0, frame_skip: int = 4,
                  render_mode: str = None, width: int = 720, height: int = 480, render_fps: int = 30,
@@ -366,14 +388,14 @@ class QuadrupedEnv(_EnvBase):
                  video_path: str = "videos/simulation.mp4", use_default_termination: bool = True, device="cuda:0"):
         if _gym is not None:
             super().__init__()
-        if save_video:
-            raise NotImplementedError("video recording is out of scope for the B200 batched path")
         self.vec = VecQuadrupedEnv(1, device=device, model_path=model_path, max_time=max_time, frame_skip=frame_skip,
                                    render_mode=render_mode, reward_fns=reward_fns, termination_fns=termination_fns,
-                                   use_default_termination=use_default_termination, auto_reset=False)
+                                   use_default_termination=use_default_termination, auto_reset=False, width=width, height=height,
+                                   render_fps=render_fps, save_video=save_video, video_path=video_path)
         self.model, self.max_time, self.frame_skip, self.render_mode = self.vec.model, max_time, frame_skip, render_mode
         self.action_space, self.observation_space = self.vec.action_space, self.vec.observation_space
-        self.data = _SingleData(self.vec)
+        from .single import SingleData
+        self.data = SingleData(self.vec)
 
     @property
     def reward_fns(self):
@@ -411,17 +433,3 @@ class QuadrupedEnv(_EnvBase):
 
     def close(self):
         self.vec.close()
-
-
-class _SingleData:
-    """numpy view of env 0 for reference-style callables (``env.data.qvel[0]`` ...)."""
-
-    def __init__(self, vec: VecQuadrupedEnv):
-        self._v = vec.data
-
-    qpos = property(lambda s: s._v.qpos[0].double().cpu().numpy())
-    qvel = property(lambda s: s._v.qvel[0].double().cpu().numpy())
-    act = property(lambda s: s._v.act[0].double().cpu().numpy())
-    ctrl = property(lambda s: s._v.ctrl[0].double().cpu().numpy())
-    sensordata = property(lambda s: s._v.sensordata[0].double().cpu().numpy())
-    time = property(lambda s: float(s._v.time[0]))

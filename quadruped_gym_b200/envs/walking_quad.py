@@ -67,14 +67,11 @@ class VecWalkingQuadrupedEnv(VecQuadrupedEnv):
         ts = self.model.opt.timestep
         self.dt = ts * self.frame_skip                                  # walking_quad.py:56
         self.window_size = int(np.ceil(2 / (1 * self.dt)))              # math_utils.py:28 with min_freq = 1
-        o = reset_options or {}
-        sample_opts = (C.c_double * 5)(float(o.get("min_speed", 0.0)), float(o.get("max_speed", 1.0)),
-                                       float(o.get("fixed_heading_angle") or 0.0), float(o.get("fixed_velocity_angle") or 0.0),
-                                       float(o.get("fixed_speed") or 0.0))
-        sample_has = (C.c_int * 3)(int(o.get("fixed_heading_angle") is not None), int(o.get("fixed_velocity_angle") is not None),
-                                   int(o.get("fixed_speed") is not None))
+        sample_opts, sample_has = self._sample_options(reset_options)
         _lib.check(_lib.lib().qg_walk_enable(self._batch, self.window_size, self.dt, ts, self.frame_skip, self.settling_time,
                                              int(self.random_controls), sample_opts, sample_has), "qg_walk_enable")
+        # key the command sampler on THIS env's seed and shard offset (global env id = env_offset + i)
+        _lib.check(_lib.lib().qg_walk_reset(self._batch, None, 1, self.seed_value, self.env_offset, self._stream()), "qg_walk_reset")
         self.control_inputs = VecVelocityHeadingControls(self)
         self.joint_centers = torch.tensor([0.0, 0.0, -0.5] * 4, dtype=torch.float32, device=self.device)
         n = self.num_envs
@@ -82,6 +79,27 @@ class VecWalkingQuadrupedEnv(VecQuadrupedEnv):
         self._wterms64 = torch.zeros((n, len(self.reward_keys)), dtype=torch.float64, device=self.device)
         self._wrew64 = torch.zeros((n,), dtype=torch.float64, device=self.device)
         self.info = {}
+
+    @staticmethod
+    def _sample_options(options: Optional[dict]):
+        """control_inputs.sample's option dict (control_inputs.py:88-92) as the two C arrays of the ABI."""
+        o = options or {}
+        sample_opts = (C.c_double * 5)(float(o.get("min_speed", 0.0)), float(o.get("max_speed", 1.0)),
+                                       float(o.get("fixed_heading_angle") or 0.0), float(o.get("fixed_velocity_angle") or 0.0),
+                                       float(o.get("fixed_speed") or 0.0))
+        sample_has = (C.c_int * 3)(int(o.get("fixed_heading_angle") is not None), int(o.get("fixed_velocity_angle") is not None),
+                                   int(o.get("fixed_speed") is not None))
+        return sample_opts, sample_has
+
+    def _walk_reset(self, m, options):
+        """WalkingQuadrupedEnv.reset bookkeeping + command resampling with `options` for this call only
+        (walking_quad.py:100-103,121-122); auto-resets inside step() keep using the constructor's reset_options."""
+        L = _lib.lib()
+        if options is not None:
+            _lib.check(L.qg_walk_set_sample_options(self._batch, *self._sample_options(options)), "qg_walk_set_sample_options")
+        _lib.check(L.qg_walk_reset(self._batch, _ptr(m), 0, self.seed_value, self.env_offset, self._stream()), "qg_walk_reset")
+        if options is not None:
+            _lib.check(L.qg_walk_set_sample_options(self._batch, *self._sample_options(self.reset_options)), "qg_walk_set_sample_options")
 
     @property
     def ideal_position(self):
@@ -98,7 +116,7 @@ class VecWalkingQuadrupedEnv(VecQuadrupedEnv):
     def reset(self, seed=None, options=None, mask: Optional[torch.Tensor] = None):
         obs, _ = super().reset(seed=seed, options=options, mask=mask)
         m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
-        _lib.check(_lib.lib().qg_walk_reset(self._batch, _ptr(m), 0, self.seed_value, self.env_offset, self._stream()), "qg_walk_reset")
+        self._walk_reset(m, options)
         self.info = {}
         return obs, self.info
 

@@ -82,11 +82,15 @@ def test_contact_sets_and_constrained_acceleration(teacher_forced):
     same = (out["counts"][:, 0] == ncon) & (out["counts"][:, 1] == nefc)
     assert same.mean() >= 0.98            # contact-set flips only at fp32-vs-fp64 ties
     assert (ncon > 0).sum() >= 100 and (ncon == 0).sum() >= 20    # the sample covers both regimes
+    flip_err = 0.0
     for e, d in enumerate(ora):
-        if not same[e]:
+        err = np.abs(out["qacc"][e] - d.qacc).max() / max(1.0, np.abs(d.qacc).max())
+        if not same[e]:        # contact set differs at an fp32-vs-fp64 tie (a vertex within round-off of the margin):
+            flip_err = max(flip_err, err)       # one contact more or less, bounded instead of skipped
             continue
         tol = 1e-4 if d.nefc == 0 else 1e-3
-        assert np.abs(out["qacc"][e] - d.qacc).max() <= tol * max(1.0, np.abs(d.qacc).max()), (e, d.ncon)
+        assert err <= tol, (e, d.ncon)
+    assert flip_err <= 1.0      # never the scale of the acceleration itself
     # solver effort comparable to the oracle's
     assert out["counts"][:, 2].mean() <= np.mean([d.solver_niter for d in ora]) + 1.0
 
@@ -132,10 +136,9 @@ def test_sensordata_parity_and_lag(teacher_forced):
     n, st, st32, ctrl, out, nxt, ora = teacher_forced
     same = np.array([out["counts"][e, 0] == d.ncon for e, d in enumerate(ora)])
     for e, d in enumerate(ora):
-        if not same[e]:
-            continue
         s, g = d.sensordata.copy(), out["sensordata"][e]
-        acc_tol = 1e-3 * max(1.0, np.abs(d.qacc).max())
+        # only the accelerometer depends on the contact set; everything else is the pre-integration state
+        acc_tol = (1e-3 if same[e] else 1.0) * max(1.0, np.abs(d.qacc).max())
         assert np.abs(g[12:15] - s[12:15]).max() <= acc_tol
         s[12:15] = g[12:15] = 0
         assert np.abs(g - s).max() <= 1e-5
@@ -147,11 +150,15 @@ def test_sensordata_parity_and_lag(teacher_forced):
 def test_next_state_parity(teacher_forced, oracle_model):
     n, st, st32, ctrl, out, nxt, ora = teacher_forced
     same = np.array([out["counts"][e, 0] == d.ncon for e, d in enumerate(ora)])
+    h = 0.002
     for e in range(n):
-        if not same[e]:
-            continue
         d = _oracle_at(oracle_model, st32, st["time"], ctrl, e)
         d.step()
+        if not same[e]:       # flipped contact set: the error of one step is bounded by h * (acceleration scale), see above
+            a = max(1.0, np.abs(ora[e].qacc).max())
+            assert np.abs(nxt["qvel"][e] - d.qvel).max() <= 2 * h * a and np.abs(nxt["qpos"][e] - d.qpos).max() <= 2 * h * h * a + 1e-5
+            assert nxt["time"][e] == d.time
+            continue
         assert np.abs(nxt["qpos"][e] - d.qpos).max() <= 1e-5
         assert np.abs(nxt["act"][e] - d.act).max() <= 1e-5
         assert np.abs(nxt["qvel"][e] - d.qvel).max() <= 1e-4 * max(1.0, np.abs(d.qvel).max())
@@ -719,15 +726,19 @@ def test_argument_errors(Vec):
     env.frame_skip = 4
     with pytest.raises(RuntimeError):
         env.step(torch.zeros((5, 12), device="cuda"))          # wrong batch size
-    with pytest.raises(NotImplementedError):
-        Vec(2, "cuda:0", render_mode="human")                  # only the rgb_array MuJoCo bridge exists
-    e2 = Vec(2, "cuda:0", render_mode="rgb_array")
-    try:
-        import mujoco  # noqa: F401
-    except ImportError:
-        with pytest.raises(NotImplementedError):
-            e2.render()                                        # bridge needs the mujoco wheel: fails loudly without it
-    e2.close()
+    with pytest.raises(ValueError):
+        Vec(2, "cuda:0", render_mode="ascii")
+    for mode in ("human", "rgb_array"):
+        e2 = Vec(2, "cuda:0", render_mode=mode)                # construction never needs the renderer
+        e2.reset()
+        for _ in range(6):                                     # 48 ms of simulated time: a frame is due at 30 fps
+            e2.step(torch.zeros((2, 12), device="cuda"))
+        try:
+            import mujoco  # noqa: F401
+        except ImportError:
+            with pytest.raises(NotImplementedError):
+                e2.render()                                    # the bridge needs the mujoco wheel: fails loudly without it
+        e2.close()
     env.close()
 
 
