@@ -79,6 +79,7 @@ struct qg_batch {
     std::vector<void*> walk_allocs, po_allocs;
     bool po_on;
     QgPoState po;
+    int po_head;      // ring slot holding the oldest frame of every environment
 };
 
 extern "C" const char* qg_last_error(void) { return g_err; }
@@ -446,7 +447,17 @@ extern "C" int qg_model_load(const void* blob, size_t nbytes, qg_model** out) {
                 G.cedge0 = mesh_cadj0[me];
                 G.level = lev;
                 G.mesh = me;
+                // bounding sphere of this hull about the LINK origin (feeds link_reach)
+                double rr = 0;
+                for (int i = v0; i < v0 + vn; ++i) {
+                    double x[3];
+                    for (int a = 0; a < 3; ++a)
+                        x[a] = G.pos[a] + G.R[3 * a] * mv[3 * i] + G.R[3 * a + 1] * mv[3 * i + 1] + G.R[3 * a + 2] * mv[3 * i + 2];
+                    rr = std::fmax(rr, std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]));
+                }
+                c.link_reach[l][lev] = std::fmax(c.link_reach[l][lev], (float)(rr * 1.0001 + 1e-6 + G.margin));
             }
+            if (c.glev[l][lev] == n) c.link_reach[l][lev] = -1e30f;   // no geom at this level: always skipped
         }
         c.glev[l][QG_NLINK + 1] = n;
         c.ngeom[l] = n;
@@ -943,6 +954,9 @@ extern "C" int qg_walk_enable(qg_batch* b, int window, double dt, double timeste
     rc |= walk_alloc(b->walk_allocs, &W.prev_sample, 12 * n); rc |= walk_alloc(b->walk_allocs, &W.f_est, 12 * n); rc |= walk_alloc(b->walk_allocs, &W.a_est, 12 * n);
     rc |= walk_alloc(b->walk_allocs, &W.prev_sign, 12 * n); rc |= walk_alloc(b->walk_allocs, &W.buffer_index, n); rc |= walk_alloc(b->walk_allocs, &W.sample_count, n);
     rc |= walk_alloc(b->walk_allocs, &W.flags, n); rc |= walk_alloc(b->walk_allocs, &W.episode, n);
+    W.blk = (int)std::ceil(std::sqrt((double)window));      // block extrema of the signal ring: 2 sqrt(window) loads per update
+    W.nblk = (window + W.blk - 1) / W.blk;
+    rc |= walk_alloc(b->walk_allocs, &W.blk_max, (size_t)W.nblk * 12 * n); rc |= walk_alloc(b->walk_allocs, &W.blk_min, (size_t)W.nblk * 12 * n);
     if (rc) return QG_ECUDA;
     QgWalkOpts& o = b->wopts;
     o.random_controls = random_controls;
@@ -1004,8 +1018,8 @@ extern "C" int qg_walk_step(qg_batch* b, float* obs_dev, const float* ctrl_dev, 
     if (!b || !b->walk_on || !obs_dev) return fail(QG_EINVAL, "qg_walk_step: bad argument");
     CUDA_OK(cudaSetDevice(b->device));
     b->wopts.auto_reset = auto_reset;
-    qg_walk_kernel<<<(b->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->walk, b->wopts, obs_dev, ctrl_dev, b->d_state, terminated_dev,
-                                                                          terminal_obs_dev, reward_dev, terms_dev, reward64_dev, terms64_dev);
+    qg_walk_kernel<<<(b->n + QG_WALK_ENVS_PER_BLOCK - 1) / QG_WALK_ENVS_PER_BLOCK, 12 * QG_WALK_ENVS_PER_BLOCK, 0, (cudaStream_t)stream>>>(
+        b->walk, b->wopts, obs_dev, ctrl_dev, b->d_state, terminated_dev, terminal_obs_dev, reward_dev, terms_dev, reward64_dev, terms64_dev);
     g_launches++;
     CUDA_OK(cudaGetLastError());
     return QG_OK;
@@ -1019,7 +1033,9 @@ extern "C" int qg_po_enable(qg_batch* b, int obs_window, double Dt, double beta,
     P.n = b->n; P.window = obs_window; P.Dt = Dt; P.beta = beta; P.settle_half = settling_time / 2;
     for (void* p : b->po_allocs) cudaFree(p);
     b->po_allocs.clear();
-    if (walk_alloc(b->po_allocs, &P.q, 4 * (size_t)b->n) || walk_alloc(b->po_allocs, &P.is_view, (size_t)b->n)) return QG_ECUDA;
+    if (walk_alloc(b->po_allocs, &P.q, 4 * (size_t)b->n) || walk_alloc(b->po_allocs, &P.is_view, (size_t)b->n) ||
+        walk_alloc(b->po_allocs, &P.ring, (size_t)b->n * obs_window * QG_PO_FRAME)) return QG_ECUDA;
+    b->po_head = 0;
     std::vector<double> q0(4 * (size_t)b->n, 0.0);
     for (int i = 0; i < b->n; ++i) q0[4 * (size_t)i] = 1.0;      // computed_orientation = [1, 0, 0, 0] (po_walking_quad.py:19)
     CUDA_OK(cudaMemcpy(P.q, q0.data(), q0.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -1031,10 +1047,11 @@ extern "C" int qg_po_observe(qg_batch* b, const float* sensordata_dev, const uin
                              float* terminal_stacked_dev, int auto_reset, int is_reset_call, void* stream) {
     if (!b || !b->po_on || !stacked_dev || (!is_reset_call && !sensordata_dev)) return fail(QG_EINVAL, "qg_po_observe: bad argument");
     CUDA_OK(cudaSetDevice(b->device));
-    qg_po_kernel<<<(b->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->po, b->walk, b->wopts, sensordata_dev ? sensordata_dev : stacked_dev,
-                                                                        b->d_state, terminated_dev, stacked_dev, terminal_stacked_dev,
-                                                                        auto_reset, is_reset_call);
+    qg_po_kernel<<<(b->n + QG_PO_ENVS_PER_BLOCK - 1) / QG_PO_ENVS_PER_BLOCK, 256, 0, (cudaStream_t)stream>>>(
+        b->po, b->walk, b->wopts, sensordata_dev ? sensordata_dev : stacked_dev, b->d_state, terminated_dev, stacked_dev,
+        terminal_stacked_dev, auto_reset, is_reset_call, b->po_head);
     g_launches++;
     CUDA_OK(cudaGetLastError());
+    if (!is_reset_call) b->po_head = (b->po_head + 1) % b->po.window;   // the slot just written was the oldest
     return QG_OK;
 }

@@ -7,7 +7,7 @@
 //   (/root/reference/src/train_quadruped.py:50) and mj_resetData + default ctrl (quadruped.py:120-124).
 #pragma once
 #ifndef QG_BLOCKSYNC
-#define QG_BLOCKSYNC 2
+#define QG_BLOCKSYNC 5
 #endif
 #include "qg_step.cuh"
 
@@ -18,7 +18,7 @@
 #define QG_MINBLOCKS 1
 #endif
 #ifndef QG_BLOCKSYNC
-#define QG_BLOCKSYNC 2
+#define QG_BLOCKSYNC 5
 #endif
 
 struct QgCounters {

@@ -83,6 +83,9 @@ struct alignas(16) QgModelC {
     int ngeom[QG_NLEG];
     int glev[QG_NLEG][5];  // geoms of lane l at tree level k are geom[l][glev[l][k] .. glev[l][k+1])
     QgGeomC geom[QG_NLEG][QG_MAXGEOM_LANE];
+    // link_reach[l][k]: no geom of lane l at tree level k can be within its margin of the plane while the link origin is
+    // higher than this above it (bounding sphere of the link's hulls about the link origin + the largest margin)
+    float link_reach[QG_NLEG][4];
     int nvert;             // hull vertices over all meshes (float4 table staged in shared memory)
     int pad_;
     // hill-climb start vertex (local id) for the support search, indexed by the cube-map cell of the

@@ -290,8 +290,9 @@ __device__ __noinline__ float2 sincos_ni(float x) {
 
 // ---------------------------------------------------------------------------------------------
 // plane-vs-hull collision (mjc_PlaneConvex restated), balanced over the WARP.
-//   pass 1 (every lane, its own geoms): oriented-box cull (20 flops each).  Survivors are pushed onto a per-warp
-//           queue in shared memory as (search direction and centre height in the MESH frame, leg, geom).
+//   pass 1 (every lane, its own geoms): link bounding-sphere reject, then an oriented-box cull (20 flops) per geom.
+//           Survivors are laid out on a per-warp queue in shared memory (positions from one warp scan of the lanes'
+//           candidate counts) as (search direction and centre height in the MESH frame, leg, geom).
 //   pass 2 (any lane, any queue entry): hill-climbing support search on the polytope-edge graph (exact for a convex
 //           hull; start vertex from a cube-map table of the direction; neighbour lists padded to int4 groups), then
 //           up to 3 hull-graph neighbours of the support vertex become extra contacts.  Works in the mesh frame only
@@ -319,14 +320,11 @@ DI WarpQueue warp_queue(float* w) {
     return q;
 }
 
-// pass 2 for one queue entry; returns the number of contacts written to out[0..3]
-DI int narrow_phase(const QgModelC& P, const float4* __restrict__ verts, const int4* __restrict__ adj4,
-                    const int4* __restrict__ cadj4, float4 e4, int meta, float4* out, int& nvert) {
-    const QgGeomC& G = P.geom[meta & 3][meta >> 2];
-    const v3 dl = V3(e4.x, e4.y, e4.z);
-    const float zc = e4.w, margin = G.margin;
+// pass 2a for one queue entry: support vertex of the hull along the search direction (hill climbing on the polytope-edge
+// graph from a cube-map start vertex).  Returns the vertex (its .w carries the list offsets) and its height along dl.
+DI float4 support_climb(const QgModelC& P, const float4* __restrict__ verts, const int4* __restrict__ cadj4, const QgGeomC& G,
+                        v3 dl, float& hbest, int& nvert) {
     const float4* __restrict__ vt = verts + G.vert0;
-    const int4* __restrict__ el = adj4 + G.edge0;
     const int4* __restrict__ cl = cadj4 + G.cedge0;
     int best;
     {
@@ -341,7 +339,7 @@ DI int narrow_phase(const QgModelC& P, const float4* __restrict__ verts, const i
         best = P.dir_start[G.mesh][((2 * a + (dm > 0.f ? 1 : 0)) * QG_DIRRES + iu) * QG_DIRRES + iv];
     }
     float4 vbest = vt[best];   // .w carries the vertex' list offsets: climb graph | hull graph << 16 (int4 units)
-    float hbest = fmaf(dl.x, vbest.x, fmaf(dl.y, vbest.y, dl.z * vbest.z));
+    hbest = fmaf(dl.x, vbest.x, fmaf(dl.y, vbest.y, dl.z * vbest.z));
     int nev = 1;
 #pragma unroll 1
     for (;;) {
@@ -355,42 +353,47 @@ DI int narrow_phase(const QgModelC& P, const float4* __restrict__ verts, const i
             float h1 = fmaf(dl.x, v1.x, fmaf(dl.y, v1.y, dl.z * v1.z));
             float h2 = fmaf(dl.x, v2.x, fmaf(dl.y, v2.y, dl.z * v2.z));
             float h3 = fmaf(dl.x, v3_.x, fmaf(dl.y, v3_.y, dl.z * v3_.z));
-            if (nb.x >= 0 && h0 < hbest) { hbest = h0; vbest = v0; best = nb.x; moved = true; }
-            if (nb.y >= 0 && h1 < hbest) { hbest = h1; vbest = v1; best = nb.y; moved = true; }
-            if (nb.z >= 0 && h2 < hbest) { hbest = h2; vbest = v2; best = nb.z; moved = true; }
-            if (nb.w >= 0 && h3 < hbest) { hbest = h3; vbest = v3_; best = nb.w; moved = true; }
+            if (nb.x >= 0 && h0 < hbest) { hbest = h0; vbest = v0; moved = true; }
+            if (nb.y >= 0 && h1 < hbest) { hbest = h1; vbest = v1; moved = true; }
+            if (nb.z >= 0 && h2 < hbest) { hbest = h2; vbest = v2; moved = true; }
+            if (nb.w >= 0 && h3 < hbest) { hbest = h3; vbest = v3_; moved = true; }
             nev += (nb.x >= 0) + (nb.y >= 0) + (nb.z >= 0) + (nb.w >= 0);
             if (nb.w < 0) break;
         }
         if (!moved) break;
     }
     nvert += nev;
-    if (zc + hbest > margin) return 0;
-    // support vertex first, then its hull-graph neighbours in list order (up to 4 candidates per geom).  A neighbour
-    // qualifies if it is within the margin and not closer than the tolerance to the candidates already taken.  Lists
-    // can be long (fan centres of flat faces: up to 104 neighbours) and nearly all entries fail the margin test, so
-    // four neighbours are fetched and tested per trip and the in-order bookkeeping runs only for the rare hits.
-    int cnt = 1, nout = 0;
-    float4 prev0 = vbest, prev1 = make_float4(0.f, 0.f, 0.f, 0.f), prev2 = prev1;
-    if (zc + hbest < margin) out[nout++] = make_float4(prev0.x, prev0.y, prev0.z, zc + hbest);  // rows only for dist < margin
-    const int4* __restrict__ e = el + ((unsigned)__float_as_int(vbest.w) >> 16);
-    const float tol2 = G.tol2;
-    const bool rule_first = P.rule_first != 0;
-    auto take = [&](float4 v, float dv) {
-        if (cnt >= 4) return;
-        float ax = v.x - prev0.x, ay = v.y - prev0.y, az = v.z - prev0.z;
-        bool ok = !(ax * ax + ay * ay + az * az < tol2);
-        if (!rule_first) {
-            float bx = v.x - prev1.x, by = v.y - prev1.y, bz = v.z - prev1.z;
-            float cx = v.x - prev2.x, cy = v.y - prev2.y, cz = v.z - prev2.z;
-            if (cnt > 1 && bx * bx + by * by + bz * bz < tol2) ok = false;
-            if (cnt > 2 && cx * cx + cy * cy + cz * cz < tol2) ok = false;
-        }
-        if (!ok) return;
-        if (cnt == 1) prev1 = v; else if (cnt == 2) prev2 = v;
-        cnt++;
-        if (dv < margin) out[nout++] = make_float4(v.x, v.y, v.z, dv);
-    };
+    return vbest;
+}
+
+// The extra plane-mesh contacts: the hull-graph neighbours of the support vertex in list order (up to 4 candidates per
+// geom).  A neighbour qualifies if it is within the margin and not closer than the tolerance to the candidates already
+// taken.  `Taken` is that bookkeeping.
+struct Taken {
+    float4 prev0, prev1, prev2;
+    int cnt, nout;
+};
+DI void taken_add(Taken& T, float4 v, float dv, float margin, float tol2, bool rule_first, float4* out) {
+    if (T.cnt >= 4) return;
+    float ax = v.x - T.prev0.x, ay = v.y - T.prev0.y, az = v.z - T.prev0.z;
+    bool ok = !(ax * ax + ay * ay + az * az < tol2);
+    if (!rule_first) {
+        float bx = v.x - T.prev1.x, by = v.y - T.prev1.y, bz = v.z - T.prev1.z;
+        float cx = v.x - T.prev2.x, cy = v.y - T.prev2.y, cz = v.z - T.prev2.z;
+        if (T.cnt > 1 && bx * bx + by * by + bz * bz < tol2) ok = false;
+        if (T.cnt > 2 && cx * cx + cy * cy + cz * cz < tol2) ok = false;
+    }
+    if (!ok) return;
+    if (T.cnt == 1) T.prev1 = v; else if (T.cnt == 2) T.prev2 = v;
+    T.cnt++;
+    if (dv < margin) out[T.nout++] = make_float4(v.x, v.y, v.z, dv);
+}
+
+// pass 2b, one lane scans its own list: lists can be long (fan centres of flat faces: up to 104 neighbours) and nearly all
+// entries fail the margin test, so four neighbours are fetched and tested per trip and the in-order bookkeeping runs only
+// for the rare hits.
+DI void scan_lane(const float4* __restrict__ vt, const int4* __restrict__ e, v3 dl, float zc, float margin, float tol2,
+                  bool rule_first, Taken& T, float4* out) {
 #pragma unroll 1
     for (;;) {
         int4 nb = __ldg(e++);
@@ -402,23 +405,39 @@ DI int narrow_phase(const QgModelC& P, const float4* __restrict__ verts, const i
         bool c0 = nb.x >= 0 && d0 <= margin, c1 = nb.y >= 0 && d1 <= margin;
         bool c2 = nb.z >= 0 && d2 <= margin, c3 = nb.w >= 0 && d3 <= margin;
         if (c0 || c1 || c2 || c3) {
-            if (c0) take(v0, d0);
-            if (c1) take(v1, d1);
-            if (c2) take(v2, d2);
-            if (c3) take(v3_, d3);
+            if (c0) taken_add(T, v0, d0, margin, tol2, rule_first, out);
+            if (c1) taken_add(T, v1, d1, margin, tol2, rule_first, out);
+            if (c2) taken_add(T, v2, d2, margin, tol2, rule_first, out);
+            if (c3) taken_add(T, v3_, d3, margin, tol2, rule_first, out);
         }
-        if (cnt >= 4 || nb.w < 0) break;
+        if (T.cnt >= 4 || nb.w < 0) break;
     }
-    return nout;
+}
+
+// pass 2 for one queue entry (any lane, any entry); returns the number of contacts written to out[0..3].
+// (A warp-cooperative version of the neighbour scan -- 32 neighbours per trip, one touching entry after the other -- was
+// measured and is slower, 1.275 against 1.229 ms: in the steady state most lanes of a warp have a touching entry.)
+DI int narrow_phase(const QgModelC& P, const float4* __restrict__ verts, const int4* __restrict__ adj4,
+                    const int4* __restrict__ cadj4, float4 e4, int meta, float4* out, int& nvert) {
+    const QgGeomC& G = P.geom[meta & 3][meta >> 2];
+    const v3 dl = V3(e4.x, e4.y, e4.z);
+    float hbest;
+    const float4 vbest = support_climb(P, verts, cadj4, G, dl, hbest, nvert);
+    const float margin = G.margin, dsup = e4.w + hbest;
+    if (dsup > margin) return 0;
+    Taken T;
+    T.prev0 = vbest; T.prev1 = T.prev2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    T.cnt = 1; T.nout = 0;
+    if (dsup < margin) out[T.nout++] = make_float4(vbest.x, vbest.y, vbest.z, dsup);  // rows only for dist < margin
+    scan_lane(verts + G.vert0, adj4 + G.edge0 + ((unsigned)__float_as_int(vbest.w) >> 16), dl, e4.w, margin, G.tol2,
+              P.rule_first != 0, T, out);
+    return T.nout;
 }
 
 DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const int4* __restrict__ adj4,
                      const int4* __restrict__ cadj4, int leg, const float* fr, v3 up, float zb, Contacts& C,
                      const WarpCounters& wc, const WarpQueue& wq, int lane) {
     __syncwarp();   // the queue aliases the quad-reduction rows: every quad of the warp is done with them
-    const int ng = P.ngeom[leg];
-    const int ngmax = max(max(P.ngeom[0], P.ngeom[1]), max(P.ngeom[2], P.ngeom[3]));
-    const unsigned lt = (1u << lane) - 1u;
     v3 dB[4];      // "up" in each link frame
     float hk[4];   // height of each link origin above the plane
 #pragma unroll
@@ -427,16 +446,71 @@ DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const 
         dB[k] = tmul(Rk, up);
         hk[k] = zb + dot(up, ld3(fr + 12 * k + 9));
     }
-    // pass 3: contacts of the result slots in `mine` (ascending = geom order)
-    auto collect = [&](unsigned mine, unsigned gs) {
+    // pass 1, lane-local: a link whose bounding sphere clears the plane takes all its geoms with it (base, femur and
+    // usually the shin of a standing robot: one compare each); the geoms of the other links go through the oriented-box
+    // cull (conservative; same contacts as any cull).  Bit g of `cand` = geom g of this lane is a candidate.
+    unsigned cand = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (hk[k] > P.link_reach[leg][k]) continue;
+        const int g1 = P.glev[leg][k + 1];
 #pragma unroll 1
-        while (mine) {
-            const int slot = __ffs(mine) - 1;
-            mine &= mine - 1;
-            const int g = gs & 7;
-            gs >>= 3;
-            const int n = wq.rcnt[slot];
-            if (n == 0) continue;
+        for (int g = P.glev[leg][k]; g < g1; ++g) {
+            const QgGeomC& G = P.geom[leg][g];
+            const float zc = hk[k] + dot(dB[k], ld3(G.pos));
+            const v3 dl = tmul(ldm3(G.R), dB[k]);  // "up" in the mesh frame
+            const float ext = fmaf(fabsf(dl.x), G.half[0], fmaf(fabsf(dl.y), G.half[1], fabsf(dl.z) * G.half[2]));
+            if (zc - ext <= G.margin) cand |= 1u << g;
+        }
+    }
+    // queue positions: the candidates of lane l occupy [off, off + n) of the warp's list, in geom order (warp scan)
+    const int n = __popc(cand);
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int off = incl - n, total = __shfl_sync(0xffffffffu, incl, 31);
+    int nvert = 0;                       // vertex evaluations of this lane's narrow phases
+    // rounds of 32 entries (one round unless the robots of this warp lie flat on the floor)
+#pragma unroll 1
+    for (int base = 0; base < total; base += 32) {
+        {   // queue entry = (search direction and centre height in the MESH frame, leg, geom)
+            unsigned c = cand;
+            int idx = off - base;
+#pragma unroll 1
+            while (c) {
+                const int g = __ffs(c) - 1;
+                c &= c - 1;
+                if (idx >= 0 && idx < 32) {
+                    const QgGeomC& G = P.geom[leg][g];
+                    const int lev = G.level;
+                    const v3 d = sel4(dB, lev);
+                    const float zc = (lev == 0 ? hk[0] : (lev == 1 ? hk[1] : (lev == 2 ? hk[2] : hk[3]))) + dot(d, ld3(G.pos));
+                    const v3 dl = tmul(ldm3(G.R), d);
+                    wq.qd[idx] = make_float4(dl.x, dl.y, dl.z, zc);
+                    wq.qmeta[idx] = leg | (g << 2);
+                }
+                idx++;
+            }
+        }
+        __syncwarp();
+        // pass 2: lane i takes queue entry i (any lane, any entry: works in the mesh frame only)
+        if (base + lane < total)
+            wq.rcnt[lane] = narrow_phase(P, verts, adj4, cadj4, wq.qd[lane], wq.qmeta[lane], wq.res + lane * 4, nvert);
+        __syncwarp();
+        // pass 3 (owner): transform the reported vertices to the base frame and append the contact records, geom order
+        unsigned c = cand;
+        int idx = off - base;
+#pragma unroll 1
+        while (c) {
+            const int g = __ffs(c) - 1;
+            c &= c - 1;
+            const int slot = idx++;
+            if (slot < 0 || slot >= 32) continue;
+            const int nres = wq.rcnt[slot];
+            if (nres == 0) continue;
             const QgGeomC& G = P.geom[leg][g];
             const int lev = G.level;
             // static indices only: `fr` stays scalarised (registers / compiler-chosen spills) instead of a local array
@@ -449,70 +523,22 @@ DI void collide_lane(const QgModelC& P, const float4* __restrict__ verts, const 
             v3 ctr = pk + mul(Rk, ld3(G.pos));
             m3 RB = matmul(Rk, ldm3(G.R));  // mesh frame -> B
 #pragma unroll 1
-            for (int k = 0; k < n; ++k) {
+            for (int k = 0; k < nres; ++k) {
                 float4 v = wq.res[slot * 4 + k];
                 if (C.n < QG_MAXCON_LANE) {
-                    int c = C.n++;
+                    int ci = C.n++;
                     float dv = v.w;
                     v3 xv = ctr + mul(RB, V3(v.x, v.y, v.z));
                     v3 xc = fma3(-0.5f * dv, up, xv);
                     float r = dv - G.margin;
                     float imp = impedance(r, G.d0, G.dmax, G.width, G.mid, G.power);
-                    C.geo[c] = make_float4(xc.x, xc.y, xc.z, 1.f / fmaxf(1e-15f, (1.f - imp) / imp * G.Rfac));
-                    C.par[c] = make_float4(G.mu, G.B, G.K * imp * r, __int_as_float(lev));
+                    C.geo[ci] = make_float4(xc.x, xc.y, xc.z, 1.f / fmaxf(1e-15f, (1.f - imp) / imp * G.Rfac));
+                    C.par[ci] = make_float4(G.mu, G.B, G.K * imp * r, __int_as_float(lev));
                 } else if (wc.count) atomicAdd(wc.row + QG_C_OVERFLOW, 1u);
             }
         }
-    };
-    int nvert = 0;                       // vertex evaluations of this lane's narrow phases
-    int qn = 0;                          // warp-uniform queue length
-    unsigned mine = 0, mine_next = 0;    // this lane's entries: slots of the batch in flight / of the carry-over
-    unsigned gs = 0, gs_next = 0;        // their geom ids, 3 bits each, in slot order
-    int nm = 0, nm_next = 0;
-    // one more trip than there are geoms: the last one only drains the queue (ONE narrow-phase site in the code)
-#pragma unroll 1
-    for (int g = 0; g <= ngmax; ++g) {
-        bool pass = false;
-        float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g < ng) {
-            const QgGeomC& G = P.geom[leg][g];
-            const int lev = G.level;
-            v3 d = sel4(dB, lev);
-            float zc = (lev == 0 ? hk[0] : (lev == 1 ? hk[1] : (lev == 2 ? hk[2] : hk[3]))) + dot(d, ld3(G.pos));
-            v3 dl = tmul(ldm3(G.R), d);  // "up" in the mesh frame
-            float ext = fmaf(fabsf(dl.x), G.half[0], fmaf(fabsf(dl.y), G.half[1], fabsf(dl.z) * G.half[2]));
-            pass = zc - ext <= G.margin;  // oriented-box cull (conservative; same contacts as any cull)
-            e4 = make_float4(dl.x, dl.y, dl.z, zc);
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (pass) {
-            const int pos = qn + __popc(m & lt);
-            wq.qd[pos] = e4;
-            wq.qmeta[pos] = leg | (g << 2);
-            if (pos < 32) { mine |= 1u << pos; gs |= (unsigned)g << (3 * nm); nm++; }
-            else { mine_next |= 1u << (pos - 32); gs_next |= (unsigned)g << (3 * nm_next); nm_next++; }
-        }
-        qn += __popc(m);
-        if (qn >= 32 || (g == ngmax && qn > 0)) {
-            const int nb = min(qn, 32);
-            // pass 2: lane i takes queue entry i
-            __syncwarp();
-            if (lane < nb)
-                wq.rcnt[lane] = narrow_phase(P, verts, adj4, cadj4, wq.qd[lane], wq.qmeta[lane], wq.res + lane * 4, nvert);
-            __syncwarp();
-            collect(mine, gs);
-            // carry the overflow entries to the front of the queue
-            float4 cd = wq.qd[32 + lane];
-            int cmeta = wq.qmeta[32 + lane];
-            __syncwarp();
-            wq.qd[lane] = cd;
-            wq.qmeta[lane] = cmeta;
-            qn -= nb;
-            mine = mine_next; gs = gs_next; nm = nm_next;
-            mine_next = 0; gs_next = 0; nm_next = 0;
-        }
+        __syncwarp();
     }
-    __syncwarp();
     wc_add(wc, QG_C_NVERT, nvert);
 }
 
@@ -776,7 +802,13 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
     bool done = false;
 #pragma unroll 1
     for (;;) {
-#if QG_BLOCKSYNC
+#if QG_BLOCKSYNC == 5
+        // experiment: warps free-run through the solver loop (warp-uniform trip count only); the block re-aligns at the
+        // substep barrier
+        if (!__any_sync(0xffffffffu, !done)) break;
+        if (done) continue;
+        arrow_solve(Hll, Hbl, Hc, Mbb, rb, rl, qr, xb, xl);
+#elif QG_BLOCKSYNC
         // block-uniform trip count: the warps of a block walk the solver code together, so that one
         // instruction-cache fill serves all of them (instruction fetch is the limiter of this kernel)
         if (!__syncthreads_or(!done)) break;

@@ -22,7 +22,11 @@ struct QgWalkState {
     double* prev_derive;         // [N]  previous_rewards_to_derive
     double* first_ctrl_cost;     // [N]  previous_ctrl_cost (set once, never updated)
     double* prev_ctrl;           // [N,12]
-    // estimator (math_utils.py:30-52); rings are [window][12][N]
+    // estimator (math_utils.py:30-52); rings are [window][12][N].  The amplitude needs max - min over the window: the ring
+    // is cut into blocks of `blk` samples whose extrema are kept ([nblk][12][N]); a step rescans only the block it writes
+    // into and combines the block extrema (2 sqrt(window) loads per channel instead of `window`; exact).
+    int blk, nblk;
+    float *blk_max, *blk_min;
     float* signal_ring;
     unsigned char* cross_ring;
     int* cross_count;            // [12][N]
@@ -68,51 +72,39 @@ __device__ void walk_sample_commands(const QgWalkState& W, const QgWalkOpts& o, 
 //   ideal position += global_velocity*timestep*frame_skip (:133), estimator.update(previous ctrl) (:136),
 //   reward = input_control_reward() on the new sensordata / ctrl (:352-422), then reset() bookkeeping
 //   (:96-126) for terminated environments when auto_reset is on.
-__global__ void qg_walk_kernel(QgWalkState W, QgWalkOpts o, float* __restrict__ obs, const float* __restrict__ ctrl,
-                               const float4* __restrict__ S, const unsigned char* __restrict__ terminated,
-                               float* __restrict__ terminal_obs, float* __restrict__ reward, float* __restrict__ terms,
-                               double* __restrict__ reward64, double* __restrict__ terms64) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+// Thread layout: a block handles 32 environments with 12 x 32 threads.  Phase 1: thread (channel k, env) updates the
+// estimator of its channel (every array is [.][12][N]: a warp touches 32 consecutive environments of one channel).
+// Phase 2: the 32 threads of channel 0 evaluate the reward terms of their environment in float64, in the reference's
+// order of operations.
+#define QG_WALK_ENVS_PER_BLOCK 32
+__global__ void __launch_bounds__(12 * QG_WALK_ENVS_PER_BLOCK)
+qg_walk_kernel(QgWalkState W, QgWalkOpts o, float* __restrict__ obs, const float* __restrict__ ctrl,
+               const float4* __restrict__ S, const unsigned char* __restrict__ terminated,
+               float* __restrict__ terminal_obs, float* __restrict__ reward, float* __restrict__ terms,
+               double* __restrict__ reward64, double* __restrict__ terms64) {
+    const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
+    const int e = blockIdx.x * QG_WALK_ENVS_PER_BLOCK + lane;
     const int N = W.n;
-    if (e >= N) return;
-    int flags = W.flags[e];
-    // ---- compute_ideal_position (walking_quad.py:88-94)
-    double* ip = W.ideal_position + 3 * (size_t)e;
-    const double* gv = W.global_velocity + 3 * (size_t)e;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) ip[k] += gv[k] * W.timestep * W.frame_skip;  // (gv*timestep)*frame_skip, left to right
-
-    // ---- OnlineFrequencyAmplitudeEstimation.update(previous data.ctrl)  (math_utils.py:57-133)
-    double c_new[12], c_prev[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) c_prev[k] = W.prev_ctrl[(size_t)e * 12 + k];
-    if (ctrl) {
-#pragma unroll
-        for (int k = 0; k < 12; ++k) c_new[k] = (double)ctrl[(size_t)e * 12 + k];
-    } else {  // data.ctrl of the batch (the step kernel ran without auto-reset, so this is the applied control)
-#pragma unroll
-        for (int l = 0; l < 4; ++l) {
-            float4 c = S[(size_t)(QG_PL_LEG0 + 4 * l + 3) * N + e];
-            c_new[3 * l] = c.x; c_new[3 * l + 1] = c.y; c_new[3 * l + 2] = c.z;
-        }
-    }
-    int idx = W.buffer_index[e], sc = W.sample_count[e];
+    const bool live = e < N;
+    int flags = 0, idx = 0, sc = 0;
     const int win = W.window;
-    if (!(flags & 4)) {
-        for (int k = 0; k < 12; ++k) {
-            W.prev_sample[(size_t)k * N + e] = c_prev[k];
-            W.signal_ring[((size_t)idx * 12 + k) * N + e] = (float)c_prev[k];
-        }
-        sc = 1;
-        idx = (idx + 1) % win;
-        flags |= 4;
-    } else {
-        if (sc < win) sc++;
-        const double dur = sc * W.dt;
-        const int lim = sc < win ? sc : win;
-        for (int k = 0; k < 12; ++k) {
-            const size_t ke = (size_t)k * N + e;
-            double diff = c_prev[k] - W.prev_sample[ke];
+    if (live) {
+        flags = W.flags[e];
+        idx = W.buffer_index[e];
+        sc = W.sample_count[e];
+        // ---- OnlineFrequencyAmplitudeEstimation.update(previous data.ctrl), channel k  (math_utils.py:57-133)
+        const double c_prev = W.prev_ctrl[(size_t)e * 12 + k];
+        const size_t ke = (size_t)k * N + e;
+        if (!(flags & 4)) {     // very first call: store the sample, no estimate yet
+            W.prev_sample[ke] = c_prev;
+            W.signal_ring[((size_t)idx * 12 + k) * N + e] = (float)c_prev;
+            W.blk_max[((size_t)(idx / W.blk) * 12 + k) * N + e] = (float)c_prev;
+            W.blk_min[((size_t)(idx / W.blk) * 12 + k) * N + e] = (float)c_prev;
+        } else {
+            const int scn = sc < win ? sc + 1 : sc;
+            const double dur = scn * W.dt;
+            const int lim = scn < win ? scn : win;
+            double diff = c_prev - W.prev_sample[ke];
             int sg = (diff > 0.0) - (diff < 0.0);
             int crossing = 0;
             if (flags & 8) {
@@ -124,24 +116,60 @@ __global__ void qg_walk_kernel(QgWalkState W, QgWalkOpts o, float* __restrict__ 
             int cc = W.cross_count[ke] - (int)W.cross_ring[ri] + crossing;
             W.cross_ring[ri] = (unsigned char)crossing;
             W.cross_count[ke] = cc;
-            W.signal_ring[ri] = (float)c_prev[k];
-            W.prev_sample[ke] = c_prev[k];
+            W.signal_ring[ri] = (float)c_prev;
+            W.prev_sample[ke] = c_prev;
             W.prev_sign[ke] = (signed char)sg;
             double f_cur = (cc / 2.0) / dur;
             W.f_est[ke] = W.ema_alpha * W.f_est[ke] + (1 - W.ema_alpha) * f_cur;
+            // amplitude = max - min over the filled part of the ring: rescan the block just written, then the block extrema
+            const int b = idx / W.blk, lo = b * W.blk;
+            int hi = lo + W.blk;
+            hi = hi < lim ? hi : lim;
             float mx = -3.0e38f, mn = 3.0e38f;
-            for (int w = 0; w < lim; ++w) {
+            for (int w = lo; w < hi; ++w) {
                 float v = W.signal_ring[((size_t)w * 12 + k) * N + e];
                 mx = fmaxf(mx, v);
                 mn = fminf(mn, v);
             }
+            W.blk_max[((size_t)b * 12 + k) * N + e] = mx;
+            W.blk_min[((size_t)b * 12 + k) * N + e] = mn;
+            const int nvalid = (lim + W.blk - 1) / W.blk;
+            for (int j = 0; j < nvalid; ++j) {
+                if (j == b) continue;
+                mx = fmaxf(mx, W.blk_max[((size_t)j * 12 + k) * N + e]);
+                mn = fminf(mn, W.blk_min[((size_t)j * 12 + k) * N + e]);
+            }
             W.a_est[ke] = W.ema_alpha * W.a_est[ke] + (1 - W.ema_alpha) * ((double)mx - (double)mn);
         }
-        idx = (idx + 1) % win;
-        flags |= 8;
     }
-    W.buffer_index[e] = idx;
+    __syncthreads();       // f_est / a_est of all 12 channels are written before the reward reads them
+    __shared__ unsigned char s_term[QG_WALK_ENVS_PER_BLOCK];
+    if (k == 0) s_term[lane] = (live && terminated && terminated[e]) ? 1 : 0;
+    if (k == 0 && live) {
+    if (!(flags & 4)) { sc = 1; flags |= 4; }
+    else { if (sc < win) sc++; flags |= 8; }
+    W.buffer_index[e] = (idx + 1) % win;
     W.sample_count[e] = sc;
+
+    // ---- compute_ideal_position (walking_quad.py:88-94)
+    double* ip = W.ideal_position + 3 * (size_t)e;
+    const double* gv = W.global_velocity + 3 * (size_t)e;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) ip[j] += gv[j] * W.timestep * W.frame_skip;  // (gv*timestep)*frame_skip, left to right
+
+    double c_new[12], c_prev[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) c_prev[j] = W.prev_ctrl[(size_t)e * 12 + j];
+    if (ctrl) {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) c_new[j] = (double)ctrl[(size_t)e * 12 + j];
+    } else {  // data.ctrl of the batch (the step kernel ran without auto-reset, so this is the applied control)
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            float4 c = S[(size_t)(QG_PL_LEG0 + 4 * l + 3) * N + e];
+            c_new[3 * l] = c.x; c_new[3 * l + 1] = c.y; c_new[3 * l + 2] = c.z;
+        }
+    }
 
     // ---- input_control_reward (walking_quad.py:352-422)
     const float* s = obs + (size_t)e * 33;
@@ -197,13 +225,9 @@ __global__ void qg_walk_kernel(QgWalkState W, QgWalkOpts o, float* __restrict__ 
     }
     for (int k = 0; k < 12; ++k) W.prev_ctrl[(size_t)e * 12 + k] = c_new[k];    // control_cost's side effect
 
-    // ---- reset() bookkeeping of WalkingQuadrupedEnv (:96-126) for terminated environments; the returned
-    //      observation becomes the reset observation (zeros), the last one is kept as terminal observation
+    // ---- reset() bookkeeping of WalkingQuadrupedEnv (:96-126) for terminated environments
     const bool term = terminated && terminated[e];
-    if (terminal_obs)
-        for (int k = 0; k < 33; ++k) terminal_obs[(size_t)e * 33 + k] = term ? obs[(size_t)e * 33 + k] : 0.f;
     if (o.auto_reset && term) {
-        for (int k = 0; k < 33; ++k) obs[(size_t)e * 33 + k] = 0.f;
         ip[0] = ip[1] = ip[2] = 0.0;
         for (int k = 0; k < 12; ++k) W.prev_ctrl[(size_t)e * 12 + k] = (double)o.joint_centers[k];
         flags &= ~1;  // previous_rewards_to_derive = None ; previous_ctrl_cost and the estimator survive
@@ -211,6 +235,18 @@ __global__ void qg_walk_kernel(QgWalkState W, QgWalkOpts o, float* __restrict__ 
         if (o.random_controls) walk_sample_commands(W, o, e, ep);
     }
     W.flags[e] = flags;
+    }
+    // ---- the returned observation of a terminated environment becomes the reset observation (zeros), the last one is
+    //      kept as terminal observation (zeros elsewhere): the block's 32 rows are contiguous, all 384 threads move them
+    __syncthreads();       // the reward threads are done reading obs
+    const int e0 = blockIdx.x * QG_WALK_ENVS_PER_BLOCK;
+    const int nrow = (N - e0 < QG_WALK_ENVS_PER_BLOCK) ? N - e0 : QG_WALK_ENVS_PER_BLOCK;
+    for (int i = threadIdx.x; i < nrow * 33; i += blockDim.x) {
+        const bool t = s_term[i / 33] != 0;
+        const size_t g = (size_t)e0 * 33 + i;
+        if (terminal_obs) terminal_obs[g] = t ? obs[g] : 0.f;
+        if (t && o.auto_reset) obs[g] = 0.f;
+    }
 }
 
 __global__ void qg_walk_reset_kernel(QgWalkState W, QgWalkOpts o, const unsigned char* __restrict__ mask, int hard) {
@@ -256,6 +292,7 @@ struct QgPoState {
     double Dt, beta, settle_half;   // timestep*frame_skip, Madgwick gain (0.033 for the IMU variant), settling_time/2
     double* q;                      // [N,4] computed_orientation
     int* is_view;                   // [N] computed_orientation aliases data.qpos[3:7] (po_walking_quad.py:68)
+    float* ring;                    // [N][window][26] frames; slot `head` (host-tracked) is the oldest of every environment
 };
 
 DI void madgwick_update_imu(double* q, const double* g, const double* a, double Dt, double beta) {
@@ -306,52 +343,98 @@ DI void po_frame(const QgPoState& P, const QgWalkState& W, int e, const float* s
     out[25] = (float)atan2(hd[1], hd[0]);                    // get_heading_theta
 }
 
-// After the physics + walking launches of one step (and BEFORE the masked physics reset):
-//   sens = sensordata of this step (terminal one for terminated envs), S = state planes (post-step, pre-reset),
-//   stacked [N, 26*window] is shifted by one frame and the new frame appended; terminated envs get their
-//   terminal stack copied to terminal_stacked and are re-filled with the reset frame (po_walking_quad.py:59-70).
-__global__ void qg_po_kernel(QgPoState P, QgWalkState W, QgWalkOpts o, const float* __restrict__ sens, const float4* __restrict__ S,
-                             const unsigned char* __restrict__ terminated, float* __restrict__ stacked,
-                             float* __restrict__ terminal_stacked, int auto_reset, int is_reset_call) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    const int N = P.n;
-    if (e >= N) return;
-    const int F = QG_PO_FRAME, Wn = P.window;
-    float* st = stacked + (size_t)e * F * Wn;
-    double* q = P.q + 4 * (size_t)e;
-    const float* s = sens + (size_t)e * 33;
-    float4 tq = S[(size_t)QG_PL_TIME * N + e];
-    double time = __hiloint2double(__float_as_int(tq.y), __float_as_int(tq.x));
-    float4 bq = S[(size_t)QG_PL_QUAT * N + e];
-    double ctrl[12];
-    for (int l = 0; l < 4; ++l) {
-        float4 c = S[(size_t)(QG_PL_LEG0 + 4 * l + 3) * N + e];
-        ctrl[3 * l] = c.x; ctrl[3 * l + 1] = c.y; ctrl[3 * l + 2] = c.z;
-    }
-    float frame[QG_PO_FRAME];
-    if (!is_reset_call) {
-        if (P.is_view[e]) { q[0] = bq.x; q[1] = bq.y; q[2] = bq.z; q[3] = bq.w; }
-        if (time > P.settle_half) {
-            double g[3] = {s[15], s[16], s[17]}, a[3] = {s[12], s[13], s[14]};
-            madgwick_update_imu(q, g, a, P.Dt, P.beta);
-            P.is_view[e] = 0;   // updateIMU returns a new array: the alias to qpos is gone
+// One POWalkingQuadrupedEnv observation per step (qg_step -> THIS -> qg_walk_step -> masked qg_reset):
+//   sens = sensordata of this step (terminal one for terminated envs), S = state planes (post-step, pre-reset).
+// The frames live in a ring [N][window][26] whose oldest slot is `head` for every environment (all environments push one
+// frame per step; a reset overwrites all slots of that environment, which is independent of the head).  A block handles
+// 32 environments: 32 threads run the filter and build the new (and, for finished environments, the reset) frame in
+// shared memory, then ALL threads write the block's contiguous rows: the new ring slot, the terminal stack of finished
+// environments, the reset fill, and the oldest-first stacked output [N, 26*window] (po_walking_quad.py:59-90) -- rows of
+// consecutive environments are contiguous, so every access is coalesced; nothing is shifted in memory.
+#define QG_PO_ENVS_PER_BLOCK 32
+__global__ void __launch_bounds__(256)
+qg_po_kernel(QgPoState P, QgWalkState W, QgWalkOpts o, const float* __restrict__ sens, const float4* __restrict__ S,
+             const unsigned char* __restrict__ terminated, float* __restrict__ stacked, float* __restrict__ terminal_stacked,
+             int auto_reset, int is_reset_call, int head) {
+    __shared__ __align__(8) float s_new[QG_PO_ENVS_PER_BLOCK][QG_PO_FRAME], s_rst[QG_PO_ENVS_PER_BLOCK][QG_PO_FRAME];
+    __shared__ unsigned char s_term[QG_PO_ENVS_PER_BLOCK];
+    const int N = P.n, Wn = P.window;
+    const int e0 = blockIdx.x * QG_PO_ENVS_PER_BLOCK;
+    const int nrow = (N - e0 < QG_PO_ENVS_PER_BLOCK) ? N - e0 : QG_PO_ENVS_PER_BLOCK;
+    if (threadIdx.x < nrow) {
+        const int e = e0 + threadIdx.x;
+        double* q = P.q + 4 * (size_t)e;
+        const bool term = is_reset_call ? (!terminated || terminated[e]) : (terminated && terminated[e]);
+        s_term[threadIdx.x] = term ? 1 : 0;
+        if (!is_reset_call) {
+            const float* s = sens + (size_t)e * 33;
+            float4 tq = S[(size_t)QG_PL_TIME * N + e];
+            double time = __hiloint2double(__float_as_int(tq.y), __float_as_int(tq.x));
+            float4 bq = S[(size_t)QG_PL_QUAT * N + e];
+            double ctrl[12];
+            for (int l = 0; l < 4; ++l) {
+                float4 c = S[(size_t)(QG_PL_LEG0 + 4 * l + 3) * N + e];
+                ctrl[3 * l] = c.x; ctrl[3 * l + 1] = c.y; ctrl[3 * l + 2] = c.z;
+            }
+            if (P.is_view[e]) { q[0] = bq.x; q[1] = bq.y; q[2] = bq.z; q[3] = bq.w; }
+            if (time > P.settle_half) {
+                double g[3] = {s[15], s[16], s[17]}, a[3] = {s[12], s[13], s[14]};
+                madgwick_update_imu(q, g, a, P.Dt, P.beta);
+                P.is_view[e] = 0;   // updateIMU returns a new array: the alias to qpos is gone
+            }
+            po_frame(P, W, e, s, ctrl, q, s_new[threadIdx.x]);
         }
-        po_frame(P, W, e, s, ctrl, q, frame);
-        for (int k = 0; k < F * (Wn - 1); ++k) st[k] = st[k + F];
-        for (int k = 0; k < F; ++k) st[F * (Wn - 1) + k] = frame[k];
+        if (term && (auto_reset || is_reset_call)) {
+            // reset(): sensordata zero, ctrl = joint centres, orientation still the stale filter state, commands not yet resampled
+            float zero[33];
+            for (int j = 0; j < 33; ++j) zero[j] = 0.f;
+            double c0[12];
+            for (int j = 0; j < 12; ++j) c0[j] = (double)o.joint_centers[j];
+            po_frame(P, W, e, zero, c0, q, s_rst[threadIdx.x]);
+            P.is_view[e] = 1;   // computed_orientation = data.qpos[3:7]
+        }
     }
-    const bool term = is_reset_call ? (!terminated || terminated[e]) : (terminated && terminated[e]);
-    if (!is_reset_call && terminal_stacked)
-        for (int k = 0; k < F * Wn; ++k) terminal_stacked[(size_t)e * F * Wn + k] = term ? st[k] : 0.f;
-    if (term && (auto_reset || is_reset_call)) {
-        // reset(): sensordata zero, ctrl = joint centres, orientation still the stale filter state, commands not yet resampled
-        float zero[33];
-        for (int k = 0; k < 33; ++k) zero[k] = 0.f;
-        double c0[12];
-        for (int k = 0; k < 12; ++k) c0[k] = (double)o.joint_centers[k];
-        po_frame(P, W, e, zero, c0, q, frame);
-        for (int w = 0; w < Wn; ++w)
-            for (int k = 0; k < F; ++k) st[w * F + k] = frame[k];
-        P.is_view[e] = 1;   // computed_orientation = data.qpos[3:7]
-    }
+    __syncthreads();
+    // All copies below move float2 (a frame is 13 of them, rows start 8-byte aligned) and walk the block's rows with
+    // incremental (environment r, frame j, pair p) indices: no division per element.
+    constexpr int FP = QG_PO_FRAME / 2;
+    static_assert(QG_PO_FRAME % 2 == 0, "frames are moved as float2");
+    const int row2 = FP * Wn, total2 = nrow * row2;
+    float2* ring2 = reinterpret_cast<float2*>(P.ring) + (size_t)e0 * row2;
+    float2* out2 = reinterpret_cast<float2*>(stacked) + (size_t)e0 * row2;
+    float2* tout2 = terminal_stacked ? reinterpret_cast<float2*>(terminal_stacked) + (size_t)e0 * row2 : nullptr;
+    const float2(*new2)[FP] = reinterpret_cast<const float2(*)[FP]>(s_new);
+    const float2(*rst2)[FP] = reinterpret_cast<const float2(*)[FP]>(s_rst);
+    const int head_new = is_reset_call ? head : (head + 1) % Wn;     // oldest slot after this push
+    const int r0 = threadIdx.x / row2, m0 = threadIdx.x - r0 * row2, j0 = m0 / FP, p0 = m0 - j0 * FP;
+    const int dr = (int)blockDim.x / row2, dm = (int)blockDim.x - dr * row2, dj = dm / FP, dp = dm - dj * FP;
+    auto for_each = [&](auto&& body) {          // body(i, r, j, p): element i = pair p of logical frame j of environment r
+        int r = r0, j = j0, p = p0;
+        for (int i = threadIdx.x; i < total2; i += blockDim.x) {
+            body(i, r, j, p);
+            p += dp; j += dj; r += dr;
+            if (p >= FP) { p -= FP; j++; }
+            if (j >= Wn) { j -= Wn; r++; }
+        }
+    };
+    // logical frame j (oldest first) of environment r after the push, BEFORE any reset fill
+    auto pushed = [&](int r, int j, int p) -> float2 {
+        if (!is_reset_call && j == Wn - 1) return new2[r][p];
+        int slot = head_new + j;
+        if (slot >= Wn) slot -= Wn;
+        return ring2[(size_t)r * row2 + slot * FP + p];
+    };
+    if (!is_reset_call && tout2)      // terminal stacks of the finished environments only
+        for_each([&](int i, int r, int j, int p) { if (s_term[r]) tout2[i] = pushed(r, j, p); });
+    for_each([&](int i, int r, int j, int p) {
+        const bool fill = s_term[r] && (auto_reset || is_reset_call);
+        if (is_reset_call && !fill) return;           // reset() touches the masked environments only
+        out2[i] = fill ? rst2[r][p] : pushed(r, j, p);
+    });
+    __syncthreads();       // every read of the old ring contents is done
+    for_each([&](int i, int r, int j, int p) {       // here j is the PHYSICAL slot of element i
+        const bool fill = s_term[r] && (auto_reset || is_reset_call);
+        if (fill) ring2[i] = rst2[r][p];
+        else if (!is_reset_call && j == head) ring2[i] = new2[r][p];
+    });
 }

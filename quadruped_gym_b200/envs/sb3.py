@@ -65,6 +65,7 @@ class LazyInfos(Sequence):
         self._col = {k: c for c, k in enumerate(self.keys)}
         self._cache = {}
         self._views = None
+        self._dicts = None
         self._done_row = {int(e): j for j, e in enumerate(np.flatnonzero(dones))} if terminal_obs is not None else {}
 
     def _column(self, key):
@@ -72,6 +73,22 @@ class LazyInfos(Sequence):
         if col is None:
             col = self._cache[key] = self.terms[:, self._col[key]].tolist()     # python floats, converted once
         return col
+
+    def _materialise(self):
+        """Plain dicts for every environment, built once in bulk: what a consumer that reads every key of every info
+        (RewardCallback._on_step) is served fastest with."""
+        if self._dicts is None:
+            rows = self.terms.tolist()
+            keys = self.keys
+            self._dicts = ds = [dict(zip(keys, row)) for row in rows]
+            for d in ds:
+                d["TimeLimit.truncated"] = False
+            for e, j in self._done_row.items():
+                ds[e]["terminal_observation"] = self.terminal_obs[j]
+        return self._dicts
+
+    def __iter__(self):
+        return iter(self._materialise())
 
     def mean(self, key) -> float:
         """Fast path for per-step logging: mean of one reward term over the environments."""
@@ -83,6 +100,8 @@ class LazyInfos(Sequence):
     def __getitem__(self, i):
         if isinstance(i, slice):
             return [self[j] for j in range(*i.indices(len(self)))]
+        if self._dicts is not None:
+            return self._dicts[i]
         if self._views is None:
             self._views = [None] * len(self)
         if i < 0:
@@ -94,7 +113,10 @@ class LazyInfos(Sequence):
 
 
 class SB3VecEnv(_VecEnvBase):
-    def __init__(self, env):
+    def __init__(self, env, copy: bool = True):
+        """``copy=False`` returns views of two alternating page-locked buffers instead of fresh arrays: valid for
+        consumers that keep an observation for at most one further step (SB3's algorithms copy into their own buffers)."""
+        self._copy = bool(copy)
         if not env.auto_reset:
             raise ValueError("SB3 VecEnv semantics need auto_reset=True")
         self.env = env
@@ -109,7 +131,8 @@ class SB3VecEnv(_VecEnvBase):
         d, k = int(env.observation_space.shape[0]), len(self.reward_keys)
         self._d, self._k = d, k
         self._packed_dev = torch.zeros((env.num_envs, d + 2 + k), dtype=torch.float32, device=env.device)
-        self._packed_host = torch.zeros((env.num_envs, d + 2 + k), dtype=torch.float32).pin_memory()
+        self._packed_hosts = [torch.zeros((env.num_envs, d + 2 + k), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._flip = 0
         self._act_host = torch.zeros((env.num_envs, 12), dtype=torch.float32).pin_memory()
 
     # -- VecEnv API -------------------------------------------------------------------------------
@@ -129,13 +152,16 @@ class SB3VecEnv(_VecEnvBase):
         p[:, d + 1].copy_(term)
         for c, key in enumerate(self.reward_keys):
             p[:, d + 2 + c].copy_(info[key])
-        self._packed_host.copy_(p, non_blocking=True)
+        self._flip ^= 1
+        host = self._packed_hosts[self._flip]
+        host.copy_(p, non_blocking=True)
         torch.cuda.current_stream(env.device).synchronize()
-        h = self._packed_host.numpy()
+        h = host.numpy()
         dones = h[:, d + 1] > 0.5
         tobs = info["terminal_observation"][term].cpu().numpy() if dones.any() else None
-        infos = LazyInfos(self.reward_keys, h[:, d + 2:].copy(), dones, tobs)
-        return h[:, :d].copy(), h[:, d].copy(), dones, infos
+        if self._copy:
+            return h[:, :d].copy(), h[:, d].copy(), dones, LazyInfos(self.reward_keys, h[:, d + 2:].copy(), dones, tobs)
+        return h[:, :d], h[:, d], dones, LazyInfos(self.reward_keys, h[:, d + 2:], dones, tobs)
 
     def step(self, actions):
         self.step_async(actions)
