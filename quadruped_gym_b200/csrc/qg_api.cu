@@ -48,7 +48,8 @@ struct Segment {
     int* d_bin_count = nullptr;   // [2][QG_NBINS] = counts, cursors
     bool perm_valid = false;
     cudaStream_t st = nullptr;    // host path only
-    cudaEvent_t done = nullptr;
+    cudaEvent_t done = nullptr;   // the segment's outputs are in the host buffers
+    cudaEvent_t binned = nullptr; // ... and its next-step permutation is built (everything on `st` is finished)
 };
 
 struct qg_batch {
@@ -501,6 +502,7 @@ static int segment_alloc(Segment& sg, bool with_stream) {
     if (with_stream) {
         CUDA_OK(cudaStreamCreateWithFlags(&sg.st, cudaStreamNonBlocking));
         CUDA_OK(cudaEventCreateWithFlags(&sg.done, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&sg.binned, cudaEventDisableTiming));
     }
     return QG_OK;
 }
@@ -508,6 +510,7 @@ static void segment_free(Segment& sg) {
     cudaFree(sg.d_bin_count); cudaFree(sg.d_chunk);
     if (sg.st) cudaStreamDestroy(sg.st);
     if (sg.done) cudaEventDestroy(sg.done);
+    if (sg.binned) cudaEventDestroy(sg.binned);
     sg = Segment();
 }
 static int reset_impl(qg_batch* b, const uint8_t* mask_dev, uint64_t seed, int random_yaw, long long env_offset,
@@ -633,13 +636,15 @@ extern "C" int qg_set_reward_table(qg_batch* b, int n_terms, const int* term_ids
 
 static inline int nblocks(int n_envs) { return (4 * n_envs + 255) / 256; }   // helper kernels: 256 threads, 4 per env
 
-// step-kernel block size: QG_BLOCK (warps of a block share instruction-cache fills through the block barriers);
-// one halving for small batches whose grid would leave SMs without a block
+// step-kernel block size: QG_BLOCK (warps of a block share instruction-cache fills through the block barriers).  Small
+// batches halve it while the halved grid still fits ONE block per SM (more SMs busy, every SM still runs a single
+// lockstep block); two desynchronised half-size blocks on one SM are slower than one full block (measured, C4: 0.716
+// against 0.633 ms), so a batch that fills more than half of the SMs keeps QG_BLOCK.
 static int step_block(const qg_batch* b, int n_envs) {
     int blk = QG_BLOCK;
     static const int forced = getenv("QG_STEP_BLOCK") ? atoi(getenv("QG_STEP_BLOCK")) : 0;   // tuning experiments
     if (forced >= 32 && forced <= QG_BLOCK && forced % 32 == 0) return forced;
-    if (blk > 128 && (4 * n_envs + blk - 1) / blk < b->num_sms) blk >>= 1;
+    while (blk > 64 && 2 * ((4 * n_envs + blk - 1) / blk) <= b->num_sms) blk >>= 1;
     return blk;
 }
 
@@ -795,13 +800,15 @@ extern "C" int qg_step_host_async(qg_batch* b, const float* action_host, int fra
         if (d_terms) CUDA_OK(cudaMemcpyAsync(terms_host + e0 * nt, d_terms + e0 * nt, c * nt * sizeof(float), cudaMemcpyDeviceToHost, sg.st));
         if (d_tobs) CUDA_OK(cudaMemcpyAsync(terminal_obs_host + e0 * 33, d_tobs + e0 * 33, c * 33 * sizeof(float), cudaMemcpyDeviceToHost, sg.st));
         CUDA_OK(cudaEventRecord(sg.done, sg.st));
-        CUDA_OK(cudaStreamWaitEvent(st, sg.done, 0));   // later work on the caller's stream sees the finished step
     }
     // binning for the next step AFTER the copies in stream order: the tiny kernels cannot start while the next segment's
-    // persistent blocks hold every SM's registers, and the D2H must not wait for them
+    // persistent blocks hold every SM's registers, and the D2H must not wait for them.  Later work on the caller's stream
+    // (a qg_step, a state read) is ordered after everything the segments did; qg_host_wait only waits for the copies.
     for (Segment& sg : b->segs) {
         rc = launch_binning(b, sg, sg.st);
         if (rc) return rc;
+        CUDA_OK(cudaEventRecord(sg.binned, sg.st));
+        CUDA_OK(cudaStreamWaitEvent(st, sg.binned, 0));
     }
     return QG_OK;
 }
@@ -809,8 +816,8 @@ extern "C" int qg_step_host_async(qg_batch* b, const float* action_host, int fra
 extern "C" int qg_host_wait(qg_batch* b, void* stream) {
     if (!b) return fail(QG_EINVAL, "batch is NULL");
     CUDA_OK(cudaSetDevice(b->device));
-    // the caller's stream already waits for every segment's `done` event: one blocking call
-    CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    (void)stream;   // outputs are complete when every segment's copies are; the caller's stream needs no host-side wait
+    for (Segment& sg : b->segs) CUDA_OK(cudaEventSynchronize(sg.done));
     return QG_OK;
 }
 

@@ -298,7 +298,7 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
         const int max_iter = opts.max_iter, ls_iter = opts.ls_iter;
 #pragma unroll 1
         for (int s = 0; s < frame_skip; ++s) {
-#if QG_BLOCKSYNC
+#if QG_BLOCKSYNC && QG_BLOCKSYNC != 6
             __syncthreads();
 #endif
             if (qsumi(shared_bad(SR) ? 1 : 0, qm) > 0) {  // mj_checkPos / mj_checkVel

@@ -802,7 +802,7 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
     bool done = false;
 #pragma unroll 1
     for (;;) {
-#if QG_BLOCKSYNC == 5
+#if QG_BLOCKSYNC >= 5
         // experiment: warps free-run through the solver loop (warp-uniform trip count only); the block re-aligns at the
         // substep barrier
         if (!__any_sync(0xffffffffu, !done)) break;
