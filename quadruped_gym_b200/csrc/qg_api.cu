@@ -365,6 +365,8 @@ extern "C" int qg_model_load(const void* blob, size_t nbytes, qg_model** out) {
         m->cadj = m->adj;
         mesh_cadj0 = mesh_adj0;
     }
+    // one group of terminators past the last list of each table: the scans prefetch the next int4 group
+    for (int i = 0; i < 4; ++i) { m->adj.push_back(-1); m->cadj.push_back(-1); }
     // the two list offsets of a vertex ride in the .w of its float4 (climb list in the low, hull list in the high half):
     // the support search reads them with the vertex instead of through one more dependent load per hop
     for (int i = 0; i < nvert; ++i) {

@@ -345,9 +345,10 @@ DI float4 support_climb(const QgModelC& P, const float4* __restrict__ verts, con
     for (;;) {
         const int4* __restrict__ e = cl + (__float_as_int(vbest.w) & 0xffff);
         bool moved = false;
+        int4 nb = __ldg(e++);
 #pragma unroll 1
         for (;;) {
-            int4 nb = __ldg(e++);
+            const int4 nxt = __ldg(e++);   // next group in flight while this one is tested (tables are padded by one group)
             float4 v0 = vt[max(nb.x, 0)], v1 = vt[max(nb.y, 0)], v2 = vt[max(nb.z, 0)], v3_ = vt[max(nb.w, 0)];
             float h0 = fmaf(dl.x, v0.x, fmaf(dl.y, v0.y, dl.z * v0.z));
             float h1 = fmaf(dl.x, v1.x, fmaf(dl.y, v1.y, dl.z * v1.z));
@@ -359,6 +360,7 @@ DI float4 support_climb(const QgModelC& P, const float4* __restrict__ verts, con
             if (nb.w >= 0 && h3 < hbest) { hbest = h3; vbest = v3_; moved = true; }
             nev += (nb.x >= 0) + (nb.y >= 0) + (nb.z >= 0) + (nb.w >= 0);
             if (nb.w < 0) break;
+            nb = nxt;
         }
         if (!moved) break;
     }
@@ -394,9 +396,10 @@ DI void taken_add(Taken& T, float4 v, float dv, float margin, float tol2, bool r
 // for the rare hits.
 DI void scan_lane(const float4* __restrict__ vt, const int4* __restrict__ e, v3 dl, float zc, float margin, float tol2,
                   bool rule_first, Taken& T, float4* out) {
+    int4 nb = __ldg(e++);
 #pragma unroll 1
     for (;;) {
-        int4 nb = __ldg(e++);
+        const int4 nxt = __ldg(e++);       // next group in flight while this one is tested (tables are padded by one group)
         float4 v0 = vt[max(nb.x, 0)], v1 = vt[max(nb.y, 0)], v2 = vt[max(nb.z, 0)], v3_ = vt[max(nb.w, 0)];
         float d0 = zc + fmaf(dl.x, v0.x, fmaf(dl.y, v0.y, dl.z * v0.z));
         float d1 = zc + fmaf(dl.x, v1.x, fmaf(dl.y, v1.y, dl.z * v1.z));
@@ -411,6 +414,7 @@ DI void scan_lane(const float4* __restrict__ vt, const int4* __restrict__ e, v3 
             if (c3) taken_add(T, v3_, d3, margin, tol2, rule_first, out);
         }
         if (T.cnt >= 4 || nb.w < 0) break;
+        nb = nxt;
     }
 }
 
