@@ -122,7 +122,7 @@ def run_reference(a):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -188,9 +188,8 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL_DEBUG stays whatever the launcher set (the driver counts ranks from NCCL's INFO lines); its log goes to
-        # stderr so that stdout stays the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL_DEBUG stays whatever the launcher set (the driver counts ranks from NCCL's INFO lines); NCCL prints to
+        # stdout, which main() has pointed at stderr so that the real stdout stays the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     envs, fs, max_time, desc = WORKLOADS[a.workload]
     if a.envs:
@@ -350,12 +349,29 @@ def run_ours(a):
                              "sample": f"{cores} processes x 1 env x 3000 env.step() (frame_skip {fs}), random actions; oracle port, not MuJoCo"},
             "counters": ctr_all,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries print there too (NCCL writes its version banner and its
+    NCCL_DEBUG lines to stdout from C), so fd 1 is pointed at stderr for the whole run and the JSON line goes to a
+    private duplicate of the original stdout.  NCCL_DEBUG is left as the launcher set it: its lines are in stderr."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+
+
+def emit(line: dict):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

@@ -8,7 +8,8 @@ this package is the thin Python host: model compiler, ctypes binding, env classe
 from . import _lib  # noqa: F401
 from .model import compile_mjcf, load_model_blob  # noqa: F401
 
-__all__ = ["VecQuadrupedEnv", "QuadrupedEnv", "VecWalkingQuadrupedEnv", "VecPOWalkingQuadrupedEnv", "SB3VecEnvAdapter",
+__all__ = ["VecQuadrupedEnv", "QuadrupedEnv", "VecWalkingQuadrupedEnv", "VecPOWalkingQuadrupedEnv", "SB3VecEnvAdapter", "SB3VecEnv",
+           "WalkingQuadrupedEnv", "POWalkingQuadrupedEnv",
            "RolloutBuffer", "rewards", "compile_mjcf", "load_model_blob"]
 
 
@@ -19,9 +20,15 @@ def __getattr__(name):  # torch is imported lazily so that the model compiler wo
     if name == "VecWalkingQuadrupedEnv":
         from .envs import walking_quad
         return walking_quad.VecWalkingQuadrupedEnv
-    if name in ("VecPOWalkingQuadrupedEnv", "SB3VecEnvAdapter"):
+    if name == "VecPOWalkingQuadrupedEnv":
         from .envs import po_walking_quad
-        return getattr(po_walking_quad, name)
+        return po_walking_quad.VecPOWalkingQuadrupedEnv
+    if name in ("SB3VecEnvAdapter", "SB3VecEnv"):
+        from .envs import sb3
+        return getattr(sb3, name)
+    if name in ("WalkingQuadrupedEnv", "POWalkingQuadrupedEnv"):
+        from .envs import single
+        return getattr(single, name)
     if name == "RolloutBuffer":
         from .rollout import RolloutBuffer
         return RolloutBuffer
