@@ -330,6 +330,8 @@ def run_ours(a):
                            l2="flushed (256 MiB write) between timed steps", preroll_steps=PREROLL,
                            parallelism=f"env-sharded x{world}, no data-path collective"),
             "clocks": clocks,
+            "step_ms": {"mean": launch_ms, "median": float(np.median(step_ms)), "min": float(np.min(step_ms)), "max": float(np.max(step_ms)),
+                        "std": float(np.std(step_ms)), "note": "per-step CUDA-event times of this rank over the timed steps"},
             "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": envs * 12 * 4,
                     "d2h_bytes_per_step": envs * (33 * 4 + 4 + 1)},
             "gpu_launches": int(launches),
