@@ -5,6 +5,7 @@ the shadow package with stub third-party modules: its ``make_env`` must resolve 
 and get as far as the device (no CUDA device here -> the library's "no CPU fallback" error)."""
 import ast
 import importlib
+import importlib.util
 import os
 import sys
 import types

@@ -3,6 +3,7 @@
 (field names / packed layouts of MjModel written from MuJoCo's public headers; the numbers underneath are the oracle's,
 so these tests prove the plumbing, not parity).  Needs the reference MJCF (this container only)."""
 import importlib
+import importlib.util
 import os
 import sys
 
