@@ -16,6 +16,7 @@ python tools/same_actions.py > $O/r2_same_actions.log 2>&1
 python tools/block_tail.py > $O/r2_block_tail.txt 2>&1
 python tools/binning_study.py > $O/r2_binning_study.txt 2>&1
 python tools/contact_profile.py > $O/r2_contact_profile.txt 2>&1
+T=40 python tools/validate_c2.py > $O/r2_validation.txt 2>&1
 python bench.py --profile --steps 20 --warmup 3 > /dev/null 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -s 500 -c 100 --csv --log-file $O/r2_launches.csv python bench.py --profile --steps 20 --warmup 3 > $O/ncu_r2_launch.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:qg_step_kernel -s 110 -c 1 -f -o $O/r2_step_kernel python bench.py --profile --steps 20 --warmup 3 > $O/ncu_r2_step.log 2>&1

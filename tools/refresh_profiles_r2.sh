@@ -4,7 +4,7 @@
 set -euo pipefail
 cd "$(dirname "${BASH_SOURCE[0]}")/.."
 for f in r2_bench.json r2_bench_c2.json r2_bench_c4.json r2_bench_c5.json r2_bench_ref.json r2_smoke.log r2_pytest_gpu.log r2_env_throughput.txt \
-         r2_e2e_sweep.txt r2_same_actions.log r2_block_tail.txt r2_binning_study.txt r2_contact_profile.txt r2_launches.csv \
+         r2_e2e_sweep.txt r2_validation.txt r2_same_actions.log r2_block_tail.txt r2_binning_study.txt r2_contact_profile.txt r2_launches.csv \
          r2_scale_2.json r2_scale_4.json r2_scale_8.json; do
   [ -f gpurun_out/$f ] && cp gpurun_out/$f profiles/$f
 done

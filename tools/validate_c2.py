@@ -1,6 +1,7 @@
 """BASELINE config 2: 4,096 envs, random actions, frame_skip 4 -- every env.step() is ALSO teacher-forced through the
 CPU oracle from the device's own pre-step state and compared (qpos, qvel, sensordata), then a soak run at 65,536 envs.
-Writes a text report (profiles/r1_validation.txt is a copy of one run)."""
+Writes a text report (profiles/r1_validation.txt / r2_validation.txt are copies of one run; the driver-visible form of the
+first half is tests/test_parity_configs_gpu.py::test_config2_every_step_teacher_forced)."""
 import os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
