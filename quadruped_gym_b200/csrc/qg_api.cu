@@ -80,7 +80,6 @@ struct qg_batch {
     std::vector<void*> walk_allocs, po_allocs;
     bool po_on;
     QgPoState po;
-    int po_head;      // ring slot holding the oldest frame of every environment
 };
 
 extern "C" const char* qg_last_error(void) { return g_err; }
@@ -1043,8 +1042,7 @@ extern "C" int qg_po_enable(qg_batch* b, int obs_window, double Dt, double beta,
     for (void* p : b->po_allocs) cudaFree(p);
     b->po_allocs.clear();
     if (walk_alloc(b->po_allocs, &P.q, 4 * (size_t)b->n) || walk_alloc(b->po_allocs, &P.is_view, (size_t)b->n) ||
-        walk_alloc(b->po_allocs, &P.ring, (size_t)b->n * obs_window * QG_PO_FRAME)) return QG_ECUDA;
-    b->po_head = 0;
+        walk_alloc(b->po_allocs, &P.ring, (size_t)b->n * obs_window * QG_PO_FRAME) || walk_alloc(b->po_allocs, &P.head_ctr, 2)) return QG_ECUDA;
     std::vector<double> q0(4 * (size_t)b->n, 0.0);
     for (int i = 0; i < b->n; ++i) q0[4 * (size_t)i] = 1.0;      // computed_orientation = [1, 0, 0, 0] (po_walking_quad.py:19)
     CUDA_OK(cudaMemcpy(P.q, q0.data(), q0.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -1058,9 +1056,8 @@ extern "C" int qg_po_observe(qg_batch* b, const float* sensordata_dev, const uin
     CUDA_OK(cudaSetDevice(b->device));
     qg_po_kernel<<<(b->n + QG_PO_ENVS_PER_BLOCK - 1) / QG_PO_ENVS_PER_BLOCK, 256, 0, (cudaStream_t)stream>>>(
         b->po, b->walk, b->wopts, sensordata_dev ? sensordata_dev : stacked_dev, b->d_state, terminated_dev, stacked_dev,
-        terminal_stacked_dev, auto_reset, is_reset_call, b->po_head);
+        terminal_stacked_dev, auto_reset, is_reset_call);
     g_launches++;
     CUDA_OK(cudaGetLastError());
-    if (!is_reset_call) b->po_head = (b->po_head + 1) % b->po.window;   // the slot just written was the oldest
     return QG_OK;
 }

@@ -292,7 +292,8 @@ struct QgPoState {
     double Dt, beta, settle_half;   // timestep*frame_skip, Madgwick gain (0.033 for the IMU variant), settling_time/2
     double* q;                      // [N,4] computed_orientation
     int* is_view;                   // [N] computed_orientation aliases data.qpos[3:7] (po_walking_quad.py:68)
-    float* ring;                    // [N][window][26] frames; slot `head` (host-tracked) is the oldest of every environment
+    float* ring;                    // [N][window][26] frames; slot head_ctr[0] is the oldest of every environment
+    int* head_ctr;                  // [2] device-side ring head and blocks-done counter (no host state: graph-capture safe)
 };
 
 DI void madgwick_update_imu(double* q, const double* g, const double* a, double Dt, double beta) {
@@ -355,7 +356,8 @@ DI void po_frame(const QgPoState& P, const QgWalkState& W, int e, const float* s
 __global__ void __launch_bounds__(256)
 qg_po_kernel(QgPoState P, QgWalkState W, QgWalkOpts o, const float* __restrict__ sens, const float4* __restrict__ S,
              const unsigned char* __restrict__ terminated, float* __restrict__ stacked, float* __restrict__ terminal_stacked,
-             int auto_reset, int is_reset_call, int head) {
+             int auto_reset, int is_reset_call) {
+    const int head = P.head_ctr[0];     // the same for every block: only the last block to finish advances it
     __shared__ __align__(8) float s_new[QG_PO_ENVS_PER_BLOCK][QG_PO_FRAME], s_rst[QG_PO_ENVS_PER_BLOCK][QG_PO_FRAME];
     __shared__ unsigned char s_term[QG_PO_ENVS_PER_BLOCK];
     const int N = P.n, Wn = P.window;
@@ -437,4 +439,12 @@ qg_po_kernel(QgPoState P, QgWalkState W, QgWalkOpts o, const float* __restrict__
         if (fill) ring2[i] = rst2[r][p];
         else if (!is_reset_call && j == head) ring2[i] = new2[r][p];
     });
+    // the slot just written was the oldest: the last block to leave advances the head (every block has read it by then)
+    if (!is_reset_call && threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(P.head_ctr + 1, 1) == (int)gridDim.x - 1) {
+            P.head_ctr[1] = 0;
+            P.head_ctr[0] = head_new;
+        }
+    }
 }

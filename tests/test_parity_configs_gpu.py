@@ -317,3 +317,33 @@ def test_pipelined_host_path_equals_device_path(Vec, monkeypatch, segments, n):
     cd.pop("verts_tested"); ch.pop("verts_tested")      # a statistic that depends on which lane served a queue entry (shadow quads)
     assert cd == ch and cd["physics_steps"] == n * T * 4
     dev.close(); host.close()
+
+
+def test_po_env_step_replays_from_a_cuda_graph(Vec):
+    """The walking / PO launches keep no host state per step (the observation ring's head is advanced on the device), so a
+    captured VecPOWalkingQuadrupedEnv.step replays: graph replays and eager calls give identical bits through auto-resets."""
+    from quadruped_gym_b200.envs.po_walking_quad import VecPOWalkingQuadrupedEnv as PO
+    n = 300
+    kw = dict(obs_window=4, frame_skip=10, max_time=0.12, random_controls=True, random_init=True, seed=3)
+    a, b = PO(n, "cuda:0", **kw), PO(n, "cuda:0", **kw)
+    a.reset(); b.reset()
+    rng = np.random.default_rng(9)
+    acts = [torch.from_numpy(rng.uniform(-1, 1, (n, 12)).astype(np.float32)).cuda() for _ in range(5)]
+    for t in range(3):                      # warm up both (lazy allocations happen outside the capture)
+        a.step(acts[t]); b.step(acts[t])
+    static = acts[0].clone()
+    g = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        a.step(static)
+    resets = 0
+    for t in range(14):
+        static.copy_(acts[t % 5])
+        g.replay()
+        o, r, te, _, info = b.step(acts[t % 5])
+        assert torch.equal(a._stacked, o) and torch.equal(a._reward, r) and torch.equal(a._terminated.bool(), te)
+        assert torch.equal(a._term_stacked[te], info["terminal_observation"][te])
+        resets += int(te.sum())
+    assert resets >= n
+    assert torch.equal(a.data.qpos, b.data.qpos) and torch.equal(a.control_inputs.velocity, b.control_inputs.velocity)
+    a.close(); b.close()
