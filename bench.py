@@ -249,16 +249,15 @@ def run_ours(a):
     barrier()
     t0 = time.perf_counter()
     rollout = None
-    if a.workload == "c4":   # PPO rollout collection: obs/action/reward/done of a 24-step horizon stay in HBM as [24,N,.]
-        rollout = {"obs": torch.zeros((24, envs, 33), device=dev), "act": torch.zeros((24, envs, 12), device=dev),
-                   "rew": torch.zeros((24, envs), device=dev), "done": torch.zeros((24, envs), dtype=torch.bool, device=dev)}
+    if a.workload == "c4":   # PPO rollout collection: obs/action/reward/done of a 24-step horizon stay in HBM as [T,N,.]
+        from quadruped_gym_b200.rollout import RolloutBuffer
+        rollout = RolloutBuffer(env, 24)
     for i in range(a.steps):
         flush.fill_(float(i))  # evict the state planes from L2 between timed steps
         ev[i][0].record()
         o, r, te, _, _ = env.step(pool[i % NPOOL])
         if rollout is not None:
-            t = i % 24
-            rollout["obs"][t].copy_(o); rollout["act"][t].copy_(pool[i % NPOOL]); rollout["rew"][t].copy_(r); rollout["done"][t].copy_(te)
+            rollout.store(i % 24, pool[i % NPOOL], o, r, te)
         ev[i][1].record()
     barrier()
     t1 = time.perf_counter()

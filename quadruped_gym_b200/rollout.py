@@ -22,6 +22,13 @@ class RolloutBuffer:
         self.dones = torch.zeros((horizon, n), dtype=torch.bool, device=dev)
         self._last_obs: Optional[torch.Tensor] = None
 
+    def store(self, t: int, action, obs, reward, done):
+        """Slot t of the horizon: the transition produced by one ``env.step(action)`` (device-to-device copies only)."""
+        self.actions[t].copy_(action)
+        self.rewards[t].copy_(reward)
+        self.dones[t].copy_(done)
+        self.obs[t + 1].copy_(obs)
+
     def collect(self, policy: Optional[Callable[[torch.Tensor], torch.Tensor]] = None, generator=None):
         """Run ``horizon`` env steps; ``policy(obs) -> action [N,12]`` (default: U(-1,1) random actions)."""
         env = self.env
@@ -34,10 +41,7 @@ class RolloutBuffer:
             else:
                 a = policy(self.obs[t])
             obs, rew, term, trunc, _ = env.step(a)
-            self.actions[t].copy_(a)
-            self.rewards[t].copy_(rew)
-            self.dones[t].copy_(term)
-            self.obs[t + 1].copy_(obs)
+            self.store(t, a, obs, rew, term)
         self._last_obs = self.obs[self.horizon]
         return self
 
