@@ -282,6 +282,9 @@ class VecQuadrupedEnv:
         the env (valid until the next call).  ``wait=False`` returns right after enqueueing (``host_wait()`` completes
         the step); info carries the fused reward terms / terminal observations when asked for."""
         self._sync_tables()
+        if self._pyfn or self._pyterm:
+            raise NotImplementedError("step_host evaluates fused reward / termination specs only (rewards.py); Python callables "
+                                      "need device tensors: use step()")
         a = np.ascontiguousarray(action, dtype=np.float32).reshape(self.num_envs, 12)
         n = self.num_envs
         if not hasattr(self, "_h_obs"):
