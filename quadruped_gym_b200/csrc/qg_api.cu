@@ -1054,7 +1054,8 @@ extern "C" int qg_po_observe(qg_batch* b, const float* sensordata_dev, const uin
                              float* terminal_stacked_dev, int auto_reset, int is_reset_call, void* stream) {
     if (!b || !b->po_on || !stacked_dev || (!is_reset_call && !sensordata_dev)) return fail(QG_EINVAL, "qg_po_observe: bad argument");
     CUDA_OK(cudaSetDevice(b->device));
-    qg_po_kernel<<<(b->n + QG_PO_ENVS_PER_BLOCK - 1) / QG_PO_ENVS_PER_BLOCK, 256, 0, (cudaStream_t)stream>>>(
+    static const int po_block = getenv("QG_PO_BLOCK") ? atoi(getenv("QG_PO_BLOCK")) : 256;   // tuning experiments
+    qg_po_kernel<<<(b->n + QG_PO_ENVS_PER_BLOCK - 1) / QG_PO_ENVS_PER_BLOCK, po_block, 0, (cudaStream_t)stream>>>(
         b->po, b->walk, b->wopts, sensordata_dev ? sensordata_dev : stacked_dev, b->d_state, terminated_dev, stacked_dev,
         terminal_stacked_dev, auto_reset, is_reset_call);
     g_launches++;
