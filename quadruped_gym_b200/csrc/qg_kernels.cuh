@@ -298,7 +298,9 @@ qg_step_kernel(const QgModelC* __restrict__ gm, const float4* __restrict__ gvert
         const int max_iter = opts.max_iter, ls_iter = opts.ls_iter;
 #pragma unroll 1
         for (int s = 0; s < frame_skip; ++s) {
-#if QG_BLOCKSYNC && QG_BLOCKSYNC != 6
+#if QG_BLOCKSYNC == 8 || QG_BLOCKSYNC == 9
+            qg_pair_sync();
+#elif QG_BLOCKSYNC && QG_BLOCKSYNC != 6
             __syncthreads();
 #endif
             if (qsumi(shared_bad(SR) ? 1 : 0, qm) > 0) {  // mj_checkPos / mj_checkVel

@@ -66,6 +66,17 @@ DI void state_load(const StateRef& r, LaneState& S) {
     for (int k = 0; k < 3; ++k) { S.q[k] = SLW(r, SL_Q + k); S.qd[k] = SLW(r, SL_QD + k); S.act[k] = SLW(r, SL_ACT + k); S.ctrl[k] = SLW(r, SL_CTRL + k); }
 }
 
+// experiment (QG_BLOCKSYNC 8 / 9): lockstep domain = a PAIR of warps instead of the block.  8: warps w and w + 4 (the two
+// warps of one SM sub-partition when warps are dealt round-robin), 9: warps 2k and 2k + 1 (control).
+DI void qg_pair_sync() {
+#if QG_BLOCKSYNC == 9
+    const int id = 1 + ((threadIdx.x >> 6) & 3);
+#else
+    const int id = 1 + ((threadIdx.x >> 5) & 3);
+#endif
+    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
+
 struct SensorOut {
     float jq[3];
     v3 acc, gyro, pos, linvel, xaxis, zaxis, vel;
@@ -594,7 +605,9 @@ DI void physics_step(const QgModelC& P, const float4* __restrict__ verts, const 
     }
     C.n = 0;
     collide_lane(P, verts, adj4, cadj4, leg, fr, up, zb, C, wc, wq, qr.lane);
-#if QG_BLOCKSYNC >= 2
+#if QG_BLOCKSYNC == 8 || QG_BLOCKSYNC == 9
+    qg_pair_sync();   // experiment: only the two warps that share an SM sub-partition re-align
+#elif QG_BLOCKSYNC >= 2
     __syncthreads();  // collision time varies per warp: re-align before the straight-line dynamics code
 #endif
 
